@@ -1,0 +1,150 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):
+    python -m oracle.gen_golden
+The reference cannot travel to the GPU box, so its outputs on fixed synthetic inputs are
+frozen here; `tests/test_oracle_golden.py` then pins `oracle/painn_oracle.py` to them and
+the `-m gpu` tests pin the CUDA path to both.
+
+Inputs are never stored: every case is regenerated from `adsorbdiff_b200.synthetic` with the
+seeds recorded in the fixture (`case` string), weights from `random_state_dict(seed=0)`.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from adsorbdiff_b200 import synthetic as S  # noqa: E402
+from oracle import painn_oracle as O  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+PROBE_ATOMS = 6  # rows of (x, vec) kept per checkpoint to keep fixtures small
+
+CHECKPOINT_CASES = ("jit2", "mixed")  # cases that keep per-layer (x, vec) probes
+CHECKPOINT_LAYERS = (0, 2, 5)
+
+SAMPLER_PARAMS = dict(num_steps=8, ads_std_low=0.1, ads_std_high=10, rot_std_low=0.01, rot_std_high=1.55)
+
+
+def cases():
+    """name -> (batch, pbc or None).  Keep in sync with tests/cases.py."""
+    from tests.cases import CASES
+
+    return CASES
+
+
+def probe_rows(n):
+    return np.unique(np.linspace(0, n - 1, PROBE_ATOMS).astype(np.int64))
+
+
+class _FakeTrainer:
+    """The 6 lines of `DenoisingTrainer` the sampler touches (sde_denoising_trainer.py:539-553)."""
+
+    def __init__(self, model):
+        self.model = model
+        self._unwrapped_model = model
+
+    @torch.no_grad()
+    def predict_denoising(self, batch, per_image=False, disable_tqdm=True):
+        p1, p2 = self.model(batch)
+        return {"positions": p1.detach(), "positions_free": p2.detach()}
+
+
+def main():
+    ns = ref_import.load()
+    os.makedirs(OUT, exist_ok=True)
+    sd = S.random_state_dict(0)
+    model = ns.PaiNN(None, 0, 1, scale_file=ns.scale_file, so3_denoising=True).eval()
+    model.load_state_dict(sd, strict=True)
+
+    for name, (make, pbc) in cases().items():
+        b = make()
+        if pbc is not None:
+            b.pbc = torch.tensor([pbc] * b.num_graphs)
+        # the reference mutates a *mutable default* pbc list (utils.py:561,568-572): reset it
+        ns.utils.radius_graph_pbc.__defaults__[-1][:] = [True, True, True]
+        rec = {}
+        # the reference formats data.id/sid/fid into its zero-neighbour error (:372-375)
+        b.id = b.fid = torch.arange(b.num_graphs)
+        sid_names, b.sid = b.sid, torch.arange(b.num_graphs)
+        try:
+            with torch.no_grad():
+                ei, neigh, d, rv, _ = model.generate_graph_values(b.clone())
+                f1, f2 = model(b.clone())
+        except ValueError as e:
+            np.savez_compressed(os.path.join(OUT, f"{name}.npz"), raises=np.array(str(e)[:40]))
+            print(name, "raises ValueError")
+            continue
+        # layer checkpoints through forward hooks on the unmodified modules
+        feats = {}
+        hooks = []
+        state = {}
+
+        def mk(tag):
+            def hook(mod, inp, out):
+                feats[tag] = (inp, out)
+            return hook
+
+        for l in range(model.num_layers):
+            hooks.append(model.message_layers[l].register_forward_hook(mk(f"msg{l}")))
+            hooks.append(model.update_layers[l].register_forward_hook(mk(f"upd{l}")))
+        with torch.no_grad():
+            model(b.clone())
+        for h in hooks:
+            h.remove()
+        rows = probe_rows(b.pos.shape[0])
+        for l in (CHECKPOINT_LAYERS if name in CHECKPOINT_CASES else ()):
+            (x_in, vec_in, *_), (dx, dvec) = feats[f"msg{l}"]
+            x = (x_in + dx) * model.inv_sqrt_2
+            vec = vec_in + dvec
+            rec[f"msg{l}.x"] = x[rows].numpy()
+            rec[f"msg{l}.vec"] = vec[rows].numpy()
+            (x_in, vec_in), (dx, dvec) = feats[f"upd{l}"]
+            sc = getattr(model, f"upd_out_scalar_scale_{l}")
+            rec[f"upd{l}.x"] = sc(x_in + dx)[rows].numpy()
+            rec[f"upd{l}.vec"] = (vec_in + dvec)[rows].numpy()
+        # how far the stock (unstable-sort) reference is from the canonical stable-tie semantics
+        g = O.generate_graph_values(b.pos.numpy(), b.cell.numpy(), b.natoms, pbc=pbc or (True, True, True))
+        same = tuple(ei.shape) == g["edge_index"].shape and bool((ei.numpy() == g["edge_index"]).all())
+        rec.update(
+            case=np.array(name), rows=rows,
+            edge_index=ei.numpy().astype(np.int32), neighbors=neigh.numpy(),
+            dist=d.numpy(), unit_vec=rv.numpy(),
+            forces=f1.numpy(), forces2=f2.numpy(),
+            n_ties=np.array(g["n_ties"]), stable_equal=np.array(same),
+        )
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **rec)
+        print(f"{name}: N={b.pos.shape[0]} E={ei.shape[1]} ties={g['n_ties']} stock==stable:{same} "
+              f"|f1|max={float(f1.abs().max()):.4g}")
+
+    # ---- sampler: unmodified Denoiser.reverse_sde_sampling_rot, 8 steps, 2 systems --------------
+    from tests.cases import sampler_batch
+
+    b = sampler_batch()
+    ns.utils.radius_graph_pbc.__defaults__[-1][:] = [True, True, True]
+    calc = ns.DiffTorchCalc(_FakeTrainer(model))
+    den = ns.Denoiser(b, calc, dict(SAMPLER_PARAMS), device="cpu", traj_dir=None, traj_names=b.sid)
+    import ase.io  # the inert shim
+
+    den.trajectories = [ase.io.Trajectory() for _ in b.sid]
+    torch.manual_seed(1234)
+    noise = torch.rand(b.num_graphs, 3)  # what :215 will draw
+    torch.manual_seed(1234)
+    den.reverse_sde_sampling_rot()
+    traj = []
+    for t in range(SAMPLER_PARAMS["num_steps"]):
+        traj.append(np.concatenate([tr.frames[t].kw["positions"] for tr in den.trajectories], 0))
+    np.savez_compressed(
+        os.path.join(OUT, "sampler.npz"), noise=noise.numpy(), traj=np.stack(traj).astype(np.float32),
+        final=b.pos.numpy(), params=np.array(repr(SAMPLER_PARAMS)),
+    )
+    print("sampler: steps", len(traj), "final pos checksum", float(b.pos.double().sum()))
+
+
+if __name__ == "__main__":
+    main()
