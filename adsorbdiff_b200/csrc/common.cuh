@@ -1,0 +1,44 @@
+// Shared helpers for the adsorbdiff_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "adsorbdiff_b200.h"
+
+#define ADK_FULL_MASK 0xffffffffu
+
+#define ADK_LAUNCH_CHECK()                         \
+    do {                                           \
+        cudaError_t e__ = cudaGetLastError();      \
+        if (e__ != cudaSuccess) return (int)e__;   \
+    } while (0)
+
+namespace adk {
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ADK_FULL_MASK, v, o);
+    return v;
+}
+
+// silu(x)/0.6  (reference: models/gemnet_oc/layers/base_layers.py:65-72)
+__device__ __forceinline__ float ssilu(float x) {
+    return (x / (1.0f + expf(-x))) * (1.0f / 0.6f);
+}
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace adk
+
+// per-translation-unit attribute setup, called by adk_init()
+int adk_neighbors_set_attrs();
+int adk_message_set_attrs();
+int adk_linear_set_attrs();

@@ -1,0 +1,444 @@
+// K1: periodic-boundary neighbour search, per-atom top-k, PBC distances, symmetrisation.
+//
+// One CTA per adsorbate+slab system; the system's atoms and its periodic-image offsets are
+// staged in shared memory.  Each warp owns target atoms: it enumerates (source j, image c)
+// in the reference's order (j-major, images in cartesian_prod order), evaluates d^2 with the
+// reference's fp32 operation order (no FMA contraction), ballot-compacts in-cutoff
+// candidates, selects the k smallest by (d^2, enumeration rank) with a bitwise radix select,
+// and keeps the directed half (j < i, or j == i with a lexicographically negative image).
+// A second phase turns the kept half + its mirror into an in-edge CSR by target atom with
+// rows ordered by (d, source, image): no floating-point atomics anywhere, deterministic.
+//
+// Reference semantics (file:line under /root/reference/adsorbdiff/):
+//   utils/utils.py:556-730   radius_graph_pbc      (candidate enumeration, d^2, cutoffs)
+//   utils/utils.py:733-853   get_max_neighbors_mask (top-k; ties -> enumeration order)
+//   utils/utils.py:513-553   get_pbc_distances
+//   models/painn/painn_denoising.py:353-400, 262-327  clamp, unit vectors, symmetrise
+#include "common.cuh"
+
+namespace {
+
+constexpr int NB_THREADS = 256;
+constexpr int NB_WARPS = NB_THREADS / 32;
+constexpr int CAND_MAX = 1024;  // per-warp candidate staging (pruned to k when it fills)
+
+struct NbParams {
+    const float* pos;
+    const float* cell;
+    const int32_t* atom_off;
+    int rep1, rep2, rep3;
+    float cutoff2;
+    int k;
+    int n_max;
+    int32_t* row_start;
+    int32_t* row_deg;
+    int32_t* e_src;
+    float4* e_geo;
+    uint32_t* kept_pack;
+    int32_t* kept_cnt;
+    int32_t* sys_counts;
+    uint32_t* status;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+struct NbSmem {
+    size_t pos, off, neg, cand_d2, cand_id, kept, kept_cnt, rev_cnt, row_start, misc, total;
+    __host__ __device__ NbSmem(int n_max, int C, int k) {
+        size_t o = 0;
+        pos = o;       o = align16(o + sizeof(float) * 3 * n_max);
+        off = o;       o = align16(o + sizeof(float) * 3 * C);
+        neg = o;       o = align16(o + C);
+        cand_d2 = o;   o = align16(o + sizeof(uint32_t) * NB_WARPS * CAND_MAX);
+        cand_id = o;   o = align16(o + sizeof(uint32_t) * NB_WARPS * CAND_MAX);
+        kept = o;      o = align16(o + sizeof(uint32_t) * (size_t)n_max * k);
+        kept_cnt = o;  o = align16(o + sizeof(int) * n_max);
+        rev_cnt = o;   o = align16(o + sizeof(int) * n_max);
+        row_start = o; o = align16(o + sizeof(int) * (n_max + 1));
+        misc = o;      o = align16(o + sizeof(int) * 4);
+        total = o;
+    }
+};
+
+// Edge geometry exactly as get_pbc_distances + generate_graph_values compute it:
+// vec = (pos_src - pos_tgt) + offset ; d = |vec| ; d <= 1e-3 -> 1e-3 ; unit = vec / d.
+__device__ __forceinline__ float4 edge_geometry(const float* s_pos, const float* s_off, int C, int tgt,
+                                                int src, int img) {
+    float vx = __fadd_rn(__fsub_rn(s_pos[3 * src + 0], s_pos[3 * tgt + 0]), s_off[img]);
+    float vy = __fadd_rn(__fsub_rn(s_pos[3 * src + 1], s_pos[3 * tgt + 1]), s_off[C + img]);
+    float vz = __fadd_rn(__fsub_rn(s_pos[3 * src + 2], s_pos[3 * tgt + 2]), s_off[2 * C + img]);
+    float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+    if (fabsf(d) <= 1.0e-3f) d = 1.0e-3f;  // torch.isclose(d, 0, atol=1e-3)  (painn_denoising.py:366-367)
+    return make_float4(d, vx / d, vy / d, vz / d);
+}
+
+// Shrink a warp's candidate list to its k smallest by (d2 bits, position), keeping order.
+// Returns the new count (== k).  Requires cnt > k.
+__device__ int prune_to_k(uint32_t* cd2, uint32_t* cid, int cnt, int k) {
+    const int lane = adk::lane_id();
+    // k-th smallest value: largest T with count(v < T) < k, built bit by bit (d2 > 0 => uint order).
+    uint32_t T = 0;
+    for (int bit = 30; bit >= 0; --bit) {
+        uint32_t trial = T | (1u << bit);
+        int c = 0;
+        for (int p = lane; p < cnt; p += 32) c += (cd2[p] < trial) ? 1 : 0;
+        c = __reduce_add_sync(ADK_FULL_MASK, c);
+        if (c < k) T = trial;
+    }
+    int n_less = 0;
+    for (int p = lane; p < cnt; p += 32) n_less += (cd2[p] < T) ? 1 : 0;
+    n_less = __reduce_add_sync(ADK_FULL_MASK, n_less);
+    int ties_left = k - n_less;  // ties (v == T) kept, earliest first
+    int wp = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        int p = base + lane;
+        uint32_t v = 0, id = 0;
+        bool valid = p < cnt;
+        if (valid) { v = cd2[p]; id = cid[p]; }
+        bool tie = valid && (v == T);
+        unsigned tmask = __ballot_sync(ADK_FULL_MASK, tie);
+        bool keep = valid && ((v < T) || (tie && (__popc(tmask & adk::lanemask_lt()) < ties_left)));
+        ties_left -= min(ties_left, __popc(tmask));
+        unsigned kmask = __ballot_sync(ADK_FULL_MASK, keep);
+        __syncwarp();
+        if (keep) {
+            int q = wp + __popc(kmask & adk::lanemask_lt());
+            cd2[q] = v;
+            cid[q] = id;
+        }
+        wp += __popc(kmask);
+        __syncwarp();
+    }
+    return wp;
+}
+
+__global__ void __launch_bounds__(NB_THREADS) neighbors_kernel(NbParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    const int a0 = P.atom_off[b];
+    const int n = P.atom_off[b + 1] - a0;
+    const int n1 = 2 * P.rep1 + 1, n2 = 2 * P.rep2 + 1, n3 = 2 * P.rep3 + 1;
+    const int C = n1 * n2 * n3;
+    const int k = P.k;
+    NbSmem L(P.n_max, C, k);
+    float* s_pos = reinterpret_cast<float*>(smem_raw + L.pos);
+    float* s_off = reinterpret_cast<float*>(smem_raw + L.off);  // [3][C]
+    unsigned char* s_neg = smem_raw + L.neg;
+    uint32_t* s_cd2 = reinterpret_cast<uint32_t*>(smem_raw + L.cand_d2);
+    uint32_t* s_cid = reinterpret_cast<uint32_t*>(smem_raw + L.cand_id);
+    uint32_t* s_kept = reinterpret_cast<uint32_t*>(smem_raw + L.kept);
+    int* s_kept_cnt = reinterpret_cast<int*>(smem_raw + L.kept_cnt);
+    int* s_rev_cnt = reinterpret_cast<int*>(smem_raw + L.rev_cnt);
+    int* s_row_start = reinterpret_cast<int*>(smem_raw + L.row_start);
+    int* s_misc = reinterpret_cast<int*>(smem_raw + L.misc);  // [0]=raw edge count
+
+    const int tid = threadIdx.x, lane = adk::lane_id(), warp = adk::warp_id();
+
+    // ---- phase 0: stage atoms and image offsets -------------------------------------------
+    for (int t = tid; t < 3 * n; t += NB_THREADS) s_pos[t] = P.pos[3 * (size_t)a0 + t];
+    const float* cell = P.cell + 9 * (size_t)b;
+    for (int c = tid; c < C; c += NB_THREADS) {
+        int i1 = c / (n2 * n3), r = c - i1 * (n2 * n3);
+        int i2 = r / n3, i3 = r - i2 * n3;
+        float u1 = (float)(i1 - P.rep1), u2 = (float)(i2 - P.rep2), u3 = (float)(i3 - P.rep3);
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            // order of the reference's K=3 bmm on the build image: (a1*u1 + a3*u3) + a2*u2, no FMA
+            float t0 = __fmul_rn(cell[0 + x], u1), t1 = __fmul_rn(cell[3 + x], u2), t2 = __fmul_rn(cell[6 + x], u3);
+            s_off[x * C + c] = __fadd_rn(__fadd_rn(t0, t2), t1);
+        }
+        s_neg[c] = (u1 < 0.f) || (u1 == 0.f && u2 < 0.f) || (u1 == 0.f && u2 == 0.f && u3 < 0.f);
+    }
+    for (int t = tid; t < n; t += NB_THREADS) { s_kept_cnt[t] = 0; s_rev_cnt[t] = 0; }
+    if (tid == 0) s_misc[0] = 0;
+    __syncthreads();
+
+    // ---- phase 1: candidates -> top-k -> kept half ----------------------------------------
+    uint32_t* cd2 = s_cd2 + warp * CAND_MAX;
+    uint32_t* cid = s_cid + warp * CAND_MAX;
+    const int total = n * C;
+    for (int i = warp; i < n; i += NB_WARPS) {
+        const float pix = s_pos[3 * i], piy = s_pos[3 * i + 1], piz = s_pos[3 * i + 2];
+        int cnt = 0;
+        int j = 0, c = lane;  // (j, c) of this lane's pair, advanced incrementally
+        while (c >= C) { c -= C; ++j; }
+        for (int base = 0; base < total; base += 32) {
+            bool ok = false;
+            float d2 = 0.f;
+            if (base + lane < total) {
+                float p2x = __fadd_rn(s_pos[3 * j], s_off[c]);
+                float p2y = __fadd_rn(s_pos[3 * j + 1], s_off[C + c]);
+                float p2z = __fadd_rn(s_pos[3 * j + 2], s_off[2 * C + c]);
+                float dx = __fsub_rn(pix, p2x), dy = __fsub_rn(piy, p2y), dz = __fsub_rn(piz, p2z);
+                d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                ok = (d2 <= P.cutoff2) && (d2 > 0.0001f);
+            }
+            unsigned m = __ballot_sync(ADK_FULL_MASK, ok);
+            if (m) {
+                if (cnt + 32 > CAND_MAX) {
+                    __syncwarp();
+                    if (cnt > k) cnt = prune_to_k(cd2, cid, cnt, k);
+                }
+                if (ok) {
+                    int p = cnt + __popc(m & adk::lanemask_lt());
+                    cd2[p] = __float_as_uint(d2);
+                    cid[p] = ((uint32_t)j << 16) | (uint32_t)c;
+                }
+                cnt += __popc(m);
+            }
+            c += 32;
+            while (c >= C) { c -= C; ++j; }
+        }
+        __syncwarp();
+        if (cnt > k) cnt = prune_to_k(cd2, cid, cnt, k);
+        __syncwarp();
+        // directed half: j < i, or the same atom through a lexicographically negative image
+        int nk = 0;
+        for (int base = 0; base < cnt; base += 32) {
+            int p = base + lane;
+            bool keep = false;
+            uint32_t id = 0;
+            if (p < cnt) {
+                id = cid[p];
+                int jj = (int)(id >> 16), cc = (int)(id & 0xffffu);
+                keep = (jj < i) || (jj == i && s_neg[cc]);
+            }
+            unsigned km = __ballot_sync(ADK_FULL_MASK, keep);
+            if (keep) {
+                s_kept[(size_t)i * k + nk + __popc(km & adk::lanemask_lt())] = id;
+                atomicAdd(&s_rev_cnt[id >> 16], 1);
+            }
+            nk += __popc(km);
+        }
+        if (lane == 0) {
+            s_kept_cnt[i] = nk;
+            atomicAdd(&s_misc[0], cnt);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- phase 2a: row offsets (exclusive scan of in-degrees), per-system counts ----------
+    if (warp == 0) {
+        int carry = 0;
+        for (int base = 0; base < n; base += 32) {
+            int t = base + lane;
+            int deg = (t < n) ? (s_kept_cnt[t] + s_rev_cnt[t]) : 0;
+            int incl = deg;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(ADK_FULL_MASK, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (t < n) s_row_start[t] = carry + incl - deg;
+            carry += __shfl_sync(ADK_FULL_MASK, incl, 31);
+        }
+        if (lane == 0) {
+            s_row_start[n] = carry;
+            P.sys_counts[2 * b] = s_misc[0];
+            P.sys_counts[2 * b + 1] = carry / 2;
+            if (s_misc[0] == 0) atomicOr(P.status, ADK_STATUS_EMPTY_SYSTEM);
+        }
+    }
+    __syncthreads();
+    const int edge_base = 2 * k * a0;
+    for (int t = tid; t < n; t += NB_THREADS) {
+        P.row_start[a0 + t] = edge_base + s_row_start[t];
+        P.row_deg[a0 + t] = s_kept_cnt[t] + s_rev_cnt[t];
+        P.kept_cnt[a0 + t] = s_kept_cnt[t];
+    }
+    for (int t = tid; t < n * k; t += NB_THREADS) {
+        int i = t / k, e = t - i * k;
+        if (e < s_kept_cnt[i]) P.kept_pack[(size_t)(a0 + i) * k + e] = s_kept[t];
+    }
+
+    // ---- phase 2b: fill rows, ordered by (d, source, image) -------------------------------
+    // The candidate staging is dead now; reuse it as per-warp sort scratch (64-bit keys).
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(s_cd2) + (size_t)warp * (CAND_MAX / 2);
+    static_assert(CAND_MAX / 2 >= ADK_MAX_ROW_DEGREE, "sort scratch too small");
+    for (int t = warp; t < n; t += NB_WARPS) {
+        const int deg = s_kept_cnt[t] + s_rev_cnt[t];
+        if (deg > ADK_MAX_ROW_DEGREE) {
+            if (lane == 0) atomicOr(P.status, ADK_STATUS_ROW_OVERFLOW);
+            continue;
+        }
+        int m = 0;
+        // direct in-edges: kept[t] = (j -> t, image c)
+        for (int base = 0; base < s_kept_cnt[t]; base += 32) {
+            int e = base + lane;
+            if (e < s_kept_cnt[t]) {
+                uint32_t id = s_kept[(size_t)t * k + e];
+                int src = (int)(id >> 16), img = (int)(id & 0xffffu);
+                float4 g = edge_geometry(s_pos, s_off, C, t, src, img);
+                keys[m + e] = ((unsigned long long)__float_as_uint(g.x) << 32) | ((uint32_t)src << 16) | (uint32_t)img;
+            }
+        }
+        m += s_kept_cnt[t];
+        // mirrored in-edges: every kept (t -> i, image c) becomes (i -> t, image -c); only i >= t can hold them
+        for (int i = t; i < n; ++i) {
+            const int ki = s_kept_cnt[i];
+            for (int base = 0; base < ki; base += 32) {
+                int e = base + lane;
+                bool hit = false;
+                uint32_t id = 0;
+                if (e < ki) {
+                    id = s_kept[(size_t)i * k + e];
+                    hit = ((int)(id >> 16) == t);
+                }
+                unsigned hm = __ballot_sync(ADK_FULL_MASK, hit);
+                if (hit) {
+                    int img = C - 1 - (int)(id & 0xffffu);
+                    float4 g = edge_geometry(s_pos, s_off, C, t, i, img);
+                    keys[m + __popc(hm & adk::lanemask_lt())] =
+                        ((unsigned long long)__float_as_uint(g.x) << 32) | ((uint32_t)i << 16) | (uint32_t)img;
+                }
+                m += __popc(hm);
+            }
+        }
+        __syncwarp();
+        const int start = edge_base + s_row_start[t];
+        for (int p = lane; p < deg; p += 32) {
+            unsigned long long key = keys[p];
+            int rank = 0;
+            for (int q = 0; q < deg; ++q) rank += (keys[q] < key) ? 1 : 0;
+            int src = (int)((key >> 16) & 0xffffu), img = (int)(key & 0xffffu);
+            P.e_src[start + rank] = a0 + src;
+            P.e_geo[start + rank] = edge_geometry(s_pos, s_off, C, t, src, img);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// export: the reference-ordered edge list of generate_graph_values (API parity / tests)
+// ------------------------------------------------------------------------------------------
+__global__ void edge_offsets_kernel(const int32_t* sys_counts, int B, int32_t* sys_edge_off, int64_t* neighbors) {
+    // single warp: exclusive scan of 2*kept over systems
+    const int lane = threadIdx.x;
+    int carry = 0;
+    for (int base = 0; base < B; base += 32) {
+        int b = base + lane;
+        int v = (b < B) ? 2 * sys_counts[2 * b + 1] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(ADK_FULL_MASK, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (b < B) {
+            sys_edge_off[b] = carry + incl - v;
+            neighbors[b] = v;
+        }
+        carry += __shfl_sync(ADK_FULL_MASK, incl, 31);
+    }
+    if (lane == 0) sys_edge_off[B] = carry;
+}
+
+__global__ void __launch_bounds__(256) export_edges_kernel(
+    const float* __restrict__ pos, const float* __restrict__ cell, const int32_t* __restrict__ atom_off, int rep1,
+    int rep2, int rep3, int k, const uint32_t* __restrict__ kept_pack, const int32_t* __restrict__ kept_cnt,
+    const int32_t* __restrict__ sys_counts, const int32_t* __restrict__ sys_edge_off, int64_t* edge_index,
+    int64_t e_cap, float* cell_offsets, float* dist, float* unit_vec) {
+    const int b = blockIdx.x;
+    const int a0 = atom_off[b], n = atom_off[b + 1] - a0;
+    const int n2 = 2 * rep2 + 1, n3 = 2 * rep3 + 1;
+    const int K = sys_counts[2 * b + 1];
+    const int base = sys_edge_off[b];
+    __shared__ int s_pref[ADK_MAX_ATOMS_PER_SYSTEM + 1];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < n; ++i) { s_pref[i] = acc; acc += kept_cnt[a0 + i]; }
+        s_pref[n] = acc;
+    }
+    __syncthreads();
+    const float* cl = cell + 9 * (size_t)b;
+    for (int t = threadIdx.x; t < n * k; t += blockDim.x) {
+        int i = t / k, e = t - i * k;
+        if (e >= kept_cnt[a0 + i]) continue;
+        uint32_t id = kept_pack[(size_t)(a0 + i) * k + e];
+        int j = (int)(id >> 16), c = (int)(id & 0xffffu);
+        int i1 = c / (n2 * n3), r = c - i1 * (n2 * n3);
+        int i2 = r / n3, i3 = r - i2 * n3;
+        float u1 = (float)(i1 - rep1), u2 = (float)(i2 - rep2), u3 = (float)(i3 - rep3);
+        float off[3];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            float t0 = __fmul_rn(cl[x], u1), t1 = __fmul_rn(cl[3 + x], u2), t2 = __fmul_rn(cl[6 + x], u3);
+            off[x] = __fadd_rn(__fadd_rn(t0, t2), t1);
+        }
+        const float* pj = pos + 3 * (size_t)(a0 + j);
+        const float* pi = pos + 3 * (size_t)(a0 + i);
+        float vx = __fadd_rn(__fsub_rn(pj[0], pi[0]), off[0]);
+        float vy = __fadd_rn(__fsub_rn(pj[1], pi[1]), off[1]);
+        float vz = __fadd_rn(__fsub_rn(pj[2], pi[2]), off[2]);
+        float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+        if (fabsf(d) <= 1.0e-3f) d = 1.0e-3f;
+        float rx = vx / d, ry = vy / d, rz = vz / d;
+        int64_t p = (int64_t)base + s_pref[i] + e;  // kept half
+        int64_t q = p + K;                           // mirrored half
+        if (q >= e_cap) continue;
+        edge_index[p] = a0 + j;
+        edge_index[e_cap + p] = a0 + i;
+        edge_index[q] = a0 + i;
+        edge_index[e_cap + q] = a0 + j;
+        cell_offsets[3 * p] = u1; cell_offsets[3 * p + 1] = u2; cell_offsets[3 * p + 2] = u3;
+        cell_offsets[3 * q] = -u1; cell_offsets[3 * q + 1] = -u2; cell_offsets[3 * q + 2] = -u3;
+        dist[p] = d; dist[q] = d;
+        unit_vec[3 * p] = rx; unit_vec[3 * p + 1] = ry; unit_vec[3 * p + 2] = rz;
+        unit_vec[3 * q] = -rx; unit_vec[3 * q + 1] = -ry; unit_vec[3 * q + 2] = -rz;
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t adk_neighbors_smem_bytes(int n_max, int num_images, int max_nbrs) {
+    if (n_max <= 0 || n_max > ADK_MAX_ATOMS_PER_SYSTEM || num_images <= 0 || num_images > ADK_MAX_IMAGES ||
+        max_nbrs <= 0 || max_nbrs > 256)
+        return ADK_ERANGE;
+    NbSmem L(n_max, num_images, max_nbrs);
+    if (L.total > 227 * 1024) return ADK_ERANGE;
+    return (int64_t)L.total;
+}
+
+extern "C" int adk_neighbors(const float* pos, const float* cell, const int32_t* atom_off, int B, int n_max,
+                             const int32_t rep[3], float cutoff2, int max_nbrs, int32_t* row_start,
+                             int32_t* row_deg, int32_t* e_src, float* e_geo, uint32_t* kept_pack,
+                             int32_t* kept_cnt, int32_t* sys_counts, uint32_t* status, void* stream) {
+    if (!pos || !cell || !atom_off || !rep || !row_start || !row_deg || !e_src || !e_geo || !kept_pack ||
+        !kept_cnt || !sys_counts || !status || B <= 0)
+        return ADK_EINVAL;
+    const int C = (2 * rep[0] + 1) * (2 * rep[1] + 1) * (2 * rep[2] + 1);
+    int64_t smem = adk_neighbors_smem_bytes(n_max, C, max_nbrs);
+    if (smem < 0) return (int)smem;
+    NbParams P;
+    P.pos = pos; P.cell = cell; P.atom_off = atom_off;
+    P.rep1 = rep[0]; P.rep2 = rep[1]; P.rep3 = rep[2];
+    P.cutoff2 = cutoff2; P.k = max_nbrs; P.n_max = n_max;
+    P.row_start = row_start; P.row_deg = row_deg; P.e_src = e_src; P.e_geo = reinterpret_cast<float4*>(e_geo);
+    P.kept_pack = kept_pack; P.kept_cnt = kept_cnt; P.sys_counts = sys_counts; P.status = status;
+    neighbors_kernel<<<B, NB_THREADS, (size_t)smem, adk::as_stream(stream)>>>(P);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int adk_export_edges(const float* pos, const float* cell, const int32_t* atom_off, int B,
+                                const int32_t rep[3], int max_nbrs, const uint32_t* kept_pack,
+                                const int32_t* kept_cnt, const int32_t* sys_counts, int32_t* sys_edge_off,
+                                int64_t* edge_index, int64_t e_cap, float* cell_offsets, float* dist,
+                                float* unit_vec, int64_t* neighbors, void* stream) {
+    if (!pos || !cell || !atom_off || !rep || !kept_pack || !kept_cnt || !sys_counts || !sys_edge_off ||
+        !edge_index || !cell_offsets || !dist || !unit_vec || !neighbors || B <= 0)
+        return ADK_EINVAL;
+    cudaStream_t s = adk::as_stream(stream);
+    edge_offsets_kernel<<<1, 32, 0, s>>>(sys_counts, B, sys_edge_off, neighbors);
+    ADK_LAUNCH_CHECK();
+    export_edges_kernel<<<B, 256, 0, s>>>(pos, cell, atom_off, rep[0], rep[1], rep[2], max_nbrs, kept_pack,
+                                          kept_cnt, sys_counts, sys_edge_off, edge_index, e_cap, cell_offsets,
+                                          dist, unit_vec);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
+int adk_neighbors_set_attrs() {
+    return (int)cudaFuncSetAttribute(neighbors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}

@@ -1,0 +1,452 @@
+"""PaiNN score model: the reference's module interface on top of the sm_100a kernels.
+
+Drop-in for `adsorbdiff.models.painn.painn_denoising.PaiNN`
+(reference: adsorbdiff/models/painn/painn_denoising.py:51-495): same constructor signature,
+same state-dict keys and shapes, same `forward(data)` contract -- a PyG
+`Batch` (or any attribute bag with `pos, cell, natoms, atomic_numbers[, pbc]`) in, per-atom
+`Tensor[N,3]` (or the `(translation, rotation)` pair when `so3_denoising`) out.  Selected from
+the reference's YAML by dotted path:  `model.name: adsorbdiff_b200.painn.PaiNN`
+(registry resolves dotted names, reference: adsorbdiff/utils/registry.py:236-249).
+
+The torch modules below only *hold parameters* in the reference's layout; none of their
+`forward`s run.  All arithmetic happens in the CUDA kernels reached through the C ABI
+(`_cabi.py`).  There is no CPU / eager fallback: a CPU tensor or a missing library raises.
+
+Scope: inference (sampling) forward, fp32.  The training step (autograd through the
+kernels) is row f-1 of SURVEY.md section 8 and raises NotImplementedError here.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import math
+from pathlib import Path
+from typing import Dict, Optional, Union
+
+import torch
+from torch import nn
+
+from . import _cabi
+from ._cabi import call, ptr
+
+# The reference's `radius_graph_pbc` mutates a mutable default argument
+# (reference: adsorbdiff/utils/utils.py:561,568-572): once a batch carrying `pbc` has been seen,
+# later batches without the attribute inherit its flags.  Kept for drop-in behaviour.
+_PBC_STICKY = [True, True, True]
+
+
+class ScaleFactor(nn.Module):
+    """Parameter holder for the fitted scalar (reference: adsorbdiff/modules/scaling/scale_factor.py:29-172)."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.scale_factor = nn.Parameter(torch.tensor(0.0), requires_grad=False)
+
+    @property
+    def fitted(self) -> bool:
+        return bool((self.scale_factor != 0.0).item())
+
+    def set_(self, scale) -> None:
+        self.scale_factor.fill_(float(scale))
+
+
+class _RadialBasisParams(nn.Module):
+    """Holds `rbf.offset` (reference: gemnet_oc/layers/radial_basis.py:64-82, 171-244)."""
+
+    def __init__(self, num_radial: int, cutoff: float, rbf: dict, envelope: dict) -> None:
+        super().__init__()
+        if rbf.get("name", "gaussian").lower() != "gaussian":
+            raise NotImplementedError("only the Gaussian radial basis of the shipped PaiNN configs is built")
+        if envelope.get("name", "polynomial").lower() != "polynomial":
+            raise NotImplementedError("only the polynomial envelope of the shipped PaiNN configs is built")
+        self.exponent = int(envelope.get("exponent", 5))
+        self.rbf = nn.Module()
+        self.rbf.register_buffer("offset", torch.linspace(0.0, 1.0, num_radial))
+
+
+class _AtomEmbedding(nn.Module):
+    def __init__(self, emb_size: int, num_elements: int) -> None:
+        super().__init__()
+        self.embeddings = nn.Embedding(num_elements, emb_size)
+        nn.init.uniform_(self.embeddings.weight, a=-math.sqrt(3), b=math.sqrt(3))
+
+
+def _xavier_linear(i: int, o: int, bias: bool = True) -> nn.Linear:
+    lin = nn.Linear(i, o, bias=bias)
+    nn.init.xavier_uniform_(lin.weight)
+    if bias:
+        lin.bias.data.fill_(0)
+    return lin
+
+
+class _MessageParams(nn.Module):
+    def __init__(self, h: int, num_rbf: int) -> None:
+        super().__init__()
+        self.x_proj = nn.Sequential(_xavier_linear(h, h), nn.Identity(), _xavier_linear(h, 3 * h))
+        self.rbf_proj = _xavier_linear(num_rbf, 3 * h)
+        self.x_layernorm = nn.LayerNorm(h)
+
+
+class _UpdateParams(nn.Module):
+    def __init__(self, h: int) -> None:
+        super().__init__()
+        self.vec_proj = _xavier_linear(h, 2 * h, bias=False)
+        self.xvec_proj = nn.Sequential(_xavier_linear(2 * h, h), nn.Identity(), _xavier_linear(h, 3 * h))
+
+
+class _GatedBlockParams(nn.Module):
+    def __init__(self, h: int, out: int) -> None:
+        super().__init__()
+        self.vec1_proj = _xavier_linear(h, h, bias=False)
+        self.vec2_proj = _xavier_linear(h, out, bias=False)
+        self.update_net = nn.Sequential(_xavier_linear(2 * h, h), nn.Identity(), _xavier_linear(h, 2 * out))
+
+
+class _OutputParams(nn.Module):
+    def __init__(self, h: int) -> None:
+        super().__init__()
+        self.output_network = nn.ModuleList([_GatedBlockParams(h, h // 2), _GatedBlockParams(h // 2, 1)])
+
+
+def _load_scale_dict(scale_file):
+    """reference: adsorbdiff/modules/scaling/compat.py:14-49"""
+    if not scale_file:
+        return None
+    if isinstance(scale_file, dict):
+        return scale_file
+    path = Path(scale_file)
+    if not path.exists():
+        raise ValueError(f"Scale file {path} does not exist.")
+    if path.suffix == ".pt":
+        return torch.load(path, weights_only=False)
+    if path.suffix == ".json":
+        with open(path) as f:
+            d = json.load(f)
+        d.pop("comment", None)
+        return d
+    raise ValueError(f"Unsupported scale file extension: {path.suffix}")
+
+
+class _Plan:
+    """Per-batch launch plan: segment offsets, image repeats, CSR and activation workspaces."""
+
+    pass
+
+
+class PaiNN(nn.Module):
+    def __init__(
+        self,
+        num_atoms: Optional[int],
+        bond_feat_dim: int,
+        num_targets: int = 1,
+        hidden_channels: int = 512,
+        num_layers: int = 6,
+        num_rbf: int = 128,
+        cutoff: float = 12.0,
+        max_neighbors: int = 50,
+        rbf: Dict[str, str] = {"name": "gaussian"},
+        envelope: Dict[str, Union[str, int]] = {"name": "polynomial", "exponent": 5},
+        regress_forces: bool = True,
+        direct_forces: bool = True,
+        use_pbc: bool = True,
+        otf_graph: bool = True,
+        num_elements: int = 83,
+        scale_file: Optional[Union[str, dict]] = None,
+        so3_denoising: bool = False,
+        energy_encoding=None,
+        sampling: bool = False,
+    ) -> None:
+        super().__init__()
+        self.num_atoms, self.bond_feat_dim, self.num_targets = num_atoms, bond_feat_dim, num_targets
+        self.hidden_channels = hidden_channels
+        self.num_layers = num_layers
+        self.num_rbf = num_rbf
+        self.cutoff = cutoff
+        self.max_neighbors = max_neighbors
+        self.regress_forces = regress_forces
+        self.direct_forces = direct_forces
+        self.otf_graph = otf_graph
+        self.use_pbc = use_pbc
+        self.so3_denoising = so3_denoising
+        self.sampling = sampling
+        self.symmetric_edge_symmetrization = False
+        if not (regress_forces and direct_forces and use_pbc):
+            raise NotImplementedError("built for the denoising configs: regress_forces, direct_forces, use_pbc")
+        if hidden_channels % 64 != 0:
+            raise NotImplementedError("hidden_channels must be a multiple of 64")
+
+        self.atom_emb = _AtomEmbedding(hidden_channels, num_elements)
+        self.radial_basis = _RadialBasisParams(num_rbf, cutoff, dict(rbf), dict(envelope))
+        # dead parameter of the reference (never read in forward, painn_denoising.py:110-114); kept so
+        # checkpoints load strictly.  Values come from the checkpoint, not from the element table.
+        self.atom_radii = nn.Parameter(torch.zeros(101), requires_grad=False)
+        self.message_layers = nn.ModuleList()
+        self.update_layers = nn.ModuleList()
+        if energy_encoding == "scalar":
+            # computed and discarded by the reference forward (:428-434): parameters only
+            self.energy_embedding = nn.Linear(1, hidden_channels)
+            self.concat_lin = nn.Sequential(nn.Linear(hidden_channels, hidden_channels), nn.Identity())
+        for i in range(num_layers):
+            self.message_layers.append(_MessageParams(hidden_channels, num_rbf))
+            self.update_layers.append(_UpdateParams(hidden_channels))
+            setattr(self, "upd_out_scalar_scale_%d" % i, ScaleFactor())
+        self.out_energy = nn.Sequential(
+            _xavier_linear(hidden_channels, hidden_channels // 2), nn.Identity(),
+            _xavier_linear(hidden_channels // 2, 1))
+        self.out_forces = _OutputParams(hidden_channels)
+        if self.so3_denoising:
+            self.out_forces2 = _OutputParams(hidden_channels)
+        self.inv_sqrt_2 = 1 / math.sqrt(2.0)
+
+        scales = _load_scale_dict(scale_file)
+        if scales:
+            for name, scale in scales.items():
+                mod = getattr(self, name, None)
+                if isinstance(mod, ScaleFactor):
+                    mod.set_(scale)
+                else:
+                    logging.warning(f"Scale factor {name} not found in model")
+        self._plan_cache: Optional[_Plan] = None
+
+    # ------------------------------------------------------------------ reference-facing API
+    @property
+    def num_params(self) -> int:
+        return sum(p.numel() for p in self.parameters())
+
+    def no_weight_decay(self) -> list:
+        """reference: adsorbdiff/models/base.py:129-136"""
+        return [n for n, _ in self.named_parameters() if "embedding" in n or "frequencies" in n or "bias" in n]
+
+    def __repr__(self) -> str:
+        return (f"{self.__class__.__name__}(hidden_channels={self.hidden_channels}, num_layers={self.num_layers}, "
+                f"num_rbf={self.num_rbf}, max_neighbors={self.max_neighbors}, cutoff={self.cutoff})")
+
+    # ------------------------------------------------------------------ planning
+    def _resolve_pbc(self, data):
+        pbc_attr = getattr(data, "pbc", None)
+        if pbc_attr is not None:
+            p = torch.atleast_2d(torch.as_tensor(pbc_attr)).bool().cpu()
+            for i in range(3):
+                if not bool(p[:, i].any()):
+                    _PBC_STICKY[i] = False
+                elif bool(p[:, i].all()):
+                    _PBC_STICKY[i] = True
+                else:
+                    raise RuntimeError("Different structures in the batch have different PBC configurations. "
+                                       "This is not currently supported.")
+        return tuple(_PBC_STICKY)
+
+    def _cell_repeats(self, cell: torch.Tensor, pbc) -> list:
+        """Images per lattice direction, max over the batch (reference: utils/utils.py:634-662).
+        Same torch ops as the reference, evaluated once per batch (the cell is constant while sampling)."""
+        cross23 = torch.cross(cell[:, 1], cell[:, 2], dim=-1)
+        vol = torch.sum(cell[:, 0] * cross23, dim=-1, keepdim=True)
+        reps = []
+        for k, (a, b) in enumerate(((1, 2), (2, 0), (0, 1))):
+            if pbc[k]:
+                cr = torch.cross(cell[:, a], cell[:, b], dim=-1)
+                inv = torch.norm(cr / vol, p=2, dim=-1)
+                reps.append(torch.ceil(self.cutoff * inv).max())
+            else:
+                reps.append(cell.new_zeros(()))
+        return [int(v) for v in torch.stack(reps).tolist()]
+
+    def plan(self, data) -> _Plan:
+        """Build (or reuse) the launch plan for this batch.  Reuse is keyed on tensor identity and
+        version of `natoms`, `cell` and `pbc`, which the sampler holds fixed for all its steps."""
+        natoms, cell = data.natoms, data.cell
+        if not torch.is_tensor(natoms):
+            natoms = torch.as_tensor([int(natoms)] if not hasattr(natoms, "__len__") else natoms)
+        pbc_attr = getattr(data, "pbc", None)
+        c = self._plan_cache
+        if (c is not None and c.natoms_ref is natoms and c.cell_ref is cell and c.pbc_ref is pbc_attr
+                and c.natoms_ver == natoms._version and c.cell_ver == cell._version
+                and c.device == data.pos.device):
+            return c
+        dev = data.pos.device
+        if dev.type != "cuda":
+            raise _cabi.AdkError("adsorbdiff_b200.PaiNN runs on CUDA tensors only (no CPU fallback); "
+                                 f"got data.pos on {dev}")
+        p = _Plan()
+        p.natoms_ref, p.cell_ref, p.pbc_ref = natoms, cell, pbc_attr
+        p.natoms_ver, p.cell_ver, p.device = natoms._version, cell._version, dev
+        nat = natoms.detach().to("cpu", torch.int64)
+        p.B = int(nat.numel())
+        p.N = int(nat.sum())
+        p.n_max = int(nat.max())
+        if p.n_max > _cabi.MAX_ATOMS_PER_SYSTEM:
+            raise _cabi.AdkError(f"system with {p.n_max} atoms exceeds ADK_MAX_ATOMS_PER_SYSTEM")
+        off = torch.zeros(p.B + 1, dtype=torch.int32)
+        off[1:] = torch.cumsum(nat, 0).to(torch.int32)
+        p.atom_off = off.to(dev)
+        p.natoms_cpu = nat
+        p.pbc = self._resolve_pbc(data)
+        p.rep = self._cell_repeats(cell.detach().float(), p.pbc)
+        p.num_images = (2 * p.rep[0] + 1) * (2 * p.rep[1] + 1) * (2 * p.rep[2] + 1)
+        k = self.max_neighbors
+        if _cabi.load().adk_neighbors_smem_bytes(p.n_max, p.num_images, k) < 0:
+            raise _cabi.AdkError(f"neighbour search staging does not fit: n_max={p.n_max}, images={p.num_images}, k={k}")
+        p.rep_c = _cabi.rep_array(p.rep)
+        N, F = p.N, self.hidden_channels
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        p.row_start = torch.empty(N, **i32)
+        p.row_deg = torch.empty(N, **i32)
+        p.e_src = torch.empty(2 * k * N, **i32)
+        p.e_geo = torch.empty(2 * k * N, 4, **f32)
+        p.kept_pack = torch.empty(N, k, dtype=torch.int32, device=dev)
+        p.kept_cnt = torch.empty(N, **i32)
+        p.sys_counts = torch.empty(p.B, 2, **i32)
+        p.status = torch.zeros(1, **i32)
+        # activations
+        p.x = torch.empty(N, F, **f32)
+        p.xn = torch.empty(N, F, **f32)
+        p.h1 = torch.empty(N, F, **f32)
+        p.xh = torch.empty(N, 3 * F, **f32)
+        p.vec = [torch.empty(N, 3, F, **f32), torch.empty(N, 3, F, **f32)]
+        p.vp = torch.empty(N, 3, 2 * F, **f32)
+        p.dot = torch.empty(N, F, **f32)
+        p.cat = torch.empty(N, 2 * F, **f32)
+        H = F // 2
+        p.v1p = torch.empty(N, 3, F, **f32)
+        p.v2p = torch.empty(N, 3, H, **f32)
+        p.hx = torch.empty(N, H, **f32)
+        p.hv = torch.empty(N, 3, H, **f32)
+        p.v2p2 = torch.empty(N, 3, 1, **f32)
+        p.ho2 = torch.empty(N, 2, **f32)
+        p.out = [torch.empty(N, 3, **f32), torch.empty(N, 3, **f32)]
+        self._plan_cache = p
+        return p
+
+    # ------------------------------------------------------------------ kernels
+    def _graph(self, p: _Plan, pos: torch.Tensor) -> None:
+        call("adk_neighbors", p.device, ptr(pos), ptr(p.cell_f32), ptr(p.atom_off), p.B, p.n_max, p.rep_c,
+             float(self.cutoff * self.cutoff), self.max_neighbors, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src),
+             ptr(p.e_geo), ptr(p.kept_pack), ptr(p.kept_cnt), ptr(p.sys_counts), ptr(p.status))
+
+    def _linear(self, p, A, lda, lin, M, act, C, ldc):
+        W = lin.weight
+        call("adk_linear", p.device, ptr(A), lda, ptr(W), ptr(lin.bias) if lin.bias is not None else None,
+             M, W.shape[0], W.shape[1], act, ptr(C), ldc)
+
+    def _head(self, p: _Plan, head: _OutputParams, x, vec, out) -> None:
+        N, F = p.N, self.hidden_channels
+        H = F // 2
+        b0, b1 = head.output_network[0], head.output_network[1]
+        dev = p.device
+        # block 0: F -> H
+        self._linear(p, vec, F, b0.vec1_proj, 3 * N, _cabi.ACT_NONE, p.v1p, F)
+        self._linear(p, vec, F, b0.vec2_proj, 3 * N, _cabi.ACT_NONE, p.v2p, H)
+        call("adk_head_prep", dev, ptr(x), ptr(p.v1p), N, F, ptr(p.cat))
+        self._linear(p, p.cat, 2 * F, b0.update_net[0], N, _cabi.ACT_SSILU, p.h1, F)
+        self._linear(p, p.h1, F, b0.update_net[2], N, _cabi.ACT_NONE, p.xn, F)  # (s|g), 2*H = F wide
+        call("adk_head_gate", dev, ptr(p.xn), ptr(p.v2p), N, H, ptr(p.hx), ptr(p.hv))
+        # block 1: H -> 1
+        self._linear(p, p.hv, H, b1.vec1_proj, 3 * N, _cabi.ACT_NONE, p.v1p, H)
+        self._linear(p, p.hv, H, b1.vec2_proj, 3 * N, _cabi.ACT_NONE, p.v2p2, 1)
+        call("adk_head_prep", dev, ptr(p.hx), ptr(p.v1p), N, H, ptr(p.cat))
+        self._linear(p, p.cat, 2 * H, b1.update_net[0], N, _cabi.ACT_SSILU, p.h1, H)
+        self._linear(p, p.h1, H, b1.update_net[2], N, _cabi.ACT_NONE, p.ho2, 2)
+        call("adk_head_gate", dev, ptr(p.ho2), ptr(p.v2p2), N, 1, None, ptr(out))
+
+    def _run(self, p: _Plan, z: torch.Tensor, pos: torch.Tensor, trace: Optional[dict] = None):
+        """Enqueue the whole forward on the current stream (capturable: no sync, no allocation)."""
+        N, F, R = p.N, self.hidden_channels, self.num_rbf
+        dev = p.device
+        self._graph(p, pos)
+        call("adk_embed", dev, ptr(z), ptr(self.atom_emb.embeddings.weight), self.atom_emb.embeddings.weight.shape[0],
+             N, F, ptr(p.x), None)
+        cur = 0
+        for l in range(self.num_layers):
+            m, u = self.message_layers[l], self.update_layers[l]
+            call("adk_layernorm", dev, ptr(p.x), ptr(m.x_layernorm.weight), ptr(m.x_layernorm.bias), N, F,
+                 float(m.x_layernorm.eps), ptr(p.xn))
+            self._linear(p, p.xn, F, m.x_proj[0], N, _cabi.ACT_SSILU, p.h1, F)
+            self._linear(p, p.h1, F, m.x_proj[2], N, _cabi.ACT_NONE, p.xh, 3 * F)
+            vin = p.vec[cur] if l > 0 else None  # vec == 0 before the first message
+            vout = p.vec[1 - cur]
+            call("adk_message", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(p.xh),
+                 ptr(vin) if vin is not None else None, ptr(m.rbf_proj.weight), ptr(m.rbf_proj.bias),
+                 ptr(self.radial_basis.rbf.offset), N, F, R, float(self.cutoff), self.radial_basis.exponent,
+                 ptr(p.x), ptr(vout))
+            cur = 1 - cur
+            vec = p.vec[cur]
+            if trace is not None:
+                trace[f"msg{l}.x"], trace[f"msg{l}.vec"] = p.x.clone(), vec.clone()
+            self._linear(p, vec, F, u.vec_proj, 3 * N, _cabi.ACT_NONE, p.vp, 2 * F)
+            call("adk_update_prep", dev, ptr(p.x), ptr(p.vp), N, F, ptr(p.dot), ptr(p.cat))
+            self._linear(p, p.cat, 2 * F, u.xvec_proj[0], N, _cabi.ACT_SSILU, p.h1, F)
+            self._linear(p, p.h1, F, u.xvec_proj[2], N, _cabi.ACT_NONE, p.xh, 3 * F)
+            sc = getattr(self, "upd_out_scalar_scale_%d" % l).scale_factor
+            call("adk_update_gate", dev, ptr(p.xh), ptr(p.dot), ptr(p.vp), ptr(sc), N, F, ptr(p.x), ptr(vec))
+            if trace is not None:
+                trace[f"upd{l}.x"], trace[f"upd{l}.vec"] = p.x.clone(), vec.clone()
+        vec = p.vec[cur]
+        self._head(p, self.out_forces, p.x, vec, p.out[0])
+        if self.so3_denoising:
+            self._head(p, self.out_forces2, p.x, vec, p.out[1])
+
+    def _refuse_training(self) -> None:
+        if torch.is_grad_enabled() and self.training:
+            raise NotImplementedError(
+                "adsorbdiff_b200.PaiNN implements the sampling (inference) forward; the training step "
+                "(autograd through the kernels) is not built yet -- call under torch.no_grad()/eval()")
+
+    def _prepare(self, data):
+        p = self.plan(data)
+        if self.atom_emb.embeddings.weight.device != p.device:
+            raise _cabi.AdkError("model parameters and data are on different devices")
+        p.cell_f32 = data.cell.detach().float().contiguous()
+        pos = data.pos.detach()
+        if pos.dtype != torch.float32 or not pos.is_contiguous():
+            pos = pos.float().contiguous()
+        z = data.atomic_numbers
+        if z.dtype != torch.int64:  # atoms_to_graphs.py:147 hands over float32
+            z = z.long()
+        return p, z.contiguous(), pos
+
+    def check_status(self, p: _Plan) -> None:
+        """Host-side read of the device status word (one D2H sync)."""
+        st = int(p.status.item())
+        if st:
+            p.status.zero_()
+        if st & _cabi.STATUS_EMPTY_SYSTEM:
+            counts = p.sys_counts[:, 0].cpu()
+            empty = torch.nonzero(counts == 0).flatten().tolist()
+            raise ValueError(f"An image has no neighbors: batch index={empty}")
+        if st & _cabi.STATUS_ROW_OVERFLOW:
+            raise _cabi.AdkError("an atom's in-degree exceeds ADK_MAX_ROW_DEGREE")
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, data, trace: Optional[dict] = None):
+        self._refuse_training()
+        with torch.no_grad():
+            p, z, pos = self._prepare(data)
+            self._run(p, z, pos, trace)
+            self.check_status(p)
+            if not self.so3_denoising:
+                return p.out[0].clone()
+            return p.out[0].clone(), p.out[1].clone()
+
+    @torch.no_grad()
+    def generate_graph_values(self, data):
+        """(edge_index, neighbors, edge_dist, edge_vector, id_swap=None) in the reference's edge order
+        (reference: painn_denoising.py:353-400).  `id_swap` is computed and discarded by the reference's
+        PaiNN and is not produced."""
+        p, _, pos = self._prepare(data)
+        self._graph(p, pos)
+        self.check_status(p)
+        dev, k = p.device, self.max_neighbors
+        e_cap = 2 * k * p.N
+        edge_index = torch.empty(2, e_cap, dtype=torch.int64, device=dev)
+        cell_off = torch.empty(e_cap, 3, dtype=torch.float32, device=dev)
+        dist = torch.empty(e_cap, dtype=torch.float32, device=dev)
+        unit = torch.empty(e_cap, 3, dtype=torch.float32, device=dev)
+        neighbors = torch.empty(p.B, dtype=torch.int64, device=dev)
+        sys_off = torch.empty(p.B + 1, dtype=torch.int32, device=dev)
+        call("adk_export_edges", dev, ptr(pos), ptr(p.cell_f32), ptr(p.atom_off), p.B, p.rep_c, k,
+             ptr(p.kept_pack), ptr(p.kept_cnt), ptr(p.sys_counts), ptr(sys_off), ptr(edge_index), e_cap,
+             ptr(cell_off), ptr(dist), ptr(unit), ptr(neighbors))
+        E = int(sys_off[-1].item())
+        self._last_cell_offsets = cell_off[:E]
+        return edge_index[:, :E].contiguous(), neighbors, dist[:E], unit[:E], None

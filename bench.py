@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the PaiNN denoising hot path (BASELINE.json metric: system*steps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--systems S]
+
+A "step" is one reverse-diffusion step over the rank's batch of adsorbate+slab systems: PaiNN
+forward (neighbour search, 6 message/update layers, two output heads) + the SE(3) update.
+Workload per GPU: BASELINE config "1024 systems x 100 reverse steps" (S = 1024 synthetic 82-atom
+systems, weak scaling: every rank holds its own 1024).  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the reference algorithm's CPU path (the oracle port of the pure-Python
+reference, which cannot travel to the GPU box) on the host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMPLER_PARAMS = dict(num_steps=100, ads_std_low=0.1, ads_std_high=10, rot_std_low=0.01, rot_std_high=1.55,
+                      early_stop=False)
+METRIC = "denoising_system_steps_per_sec"
+UNIT = "system*steps/s"
+
+
+# ----------------------------------------------------------------------------------------------
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_port_rate(n_systems: int, n_steps: int, threads: int):
+    """system*steps/s of the oracle port (CPU restatement of the reference) on `threads` host threads."""
+    from adsorbdiff_b200 import synthetic as S
+    from oracle import painn_oracle as O
+
+    torch.set_num_threads(threads)
+    sd = S.random_state_dict(0)
+    b = S.make_batch(n_systems)
+    fields = dict(pos=b.pos, cell=b.cell, batch=b.batch, tags=b.tags, fixed=b.fixed, natoms=b.natoms,
+                  atomic_numbers=b.atomic_numbers)
+    torch.manual_seed(0)
+    noise = torch.rand(n_systems, 3)
+    t0 = time.perf_counter()
+    O.sample(sd, fields, SAMPLER_PARAMS, noise, num_steps=n_steps)
+    dt = time.perf_counter() - t0
+    return n_systems * n_steps / dt, dt
+
+
+def run_reference(args):
+    """The reference arm: the reference algorithm's CPU path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # size the sample so that (steps + warmup) reference steps end within ~2 minutes
+    probe_rate, _ = cpu_port_rate(1, 1, cores)
+    budget_s = 120.0
+    total_steps = args.steps + args.warmup
+    n_sys = max(1, min(16, int(probe_rate * budget_s / total_steps)))
+    from adsorbdiff_b200 import synthetic as S
+    from oracle import painn_oracle as O
+
+    torch.set_num_threads(cores)
+    sd = S.random_state_dict(0)
+    b = S.make_batch(n_sys)
+    torch.manual_seed(0)
+    pos = O.init_placement(b.pos.clone(), b.cell, b.batch, b.tags, torch.rand(n_sys, 3))
+    times = []
+    for t in range(total_steps):
+        t0 = time.perf_counter()
+        tr_g, rot_g, dt = O.schedule(t % SAMPLER_PARAMS["num_steps"], SAMPLER_PARAMS)
+        s_tr, s_rot = O.painn_forward(sd, b.atomic_numbers, pos.numpy(), b.cell.numpy(), b.natoms)
+        pos, _ = O.se3_step(pos, b.cell, b.batch, b.tags, b.fixed, s_tr, s_rot, tr_g, rot_g, dt)
+        if t >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    elapsed = sum(times)
+    value = n_sys * args.steps / elapsed
+    sample = f"{n_sys} systems x {args.steps} steps of the same synthetic workload (oracle port of the reference, fp32)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.systems), "reference_sample_systems": n_sys},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(systems):
+    return (f"PaiNN reverse-diffusion sampling, {systems} synthetic OC20-Dense-shaped systems per GPU "
+            "(80-atom slab + CO/OH, 82 atoms, ~4110 edges), hidden 512 x 6 layers, 128 RBF, cutoff 12 A, 50 nbrs")
+
+
+# ----------------------------------------------------------------------------------------------
+def kernel_breakdown(model, plan, z, pos, tags, fixed, sched, step, max_upd, reps=3):
+    """Per-entry-point device time of one step, CUDA events on the launching stream."""
+    from adsorbdiff_b200 import _cabi
+
+    dev = plan.device
+    stream = torch.cuda.current_stream(dev)
+    records = []
+    orig_call = _cabi.call
+
+    def timed_call(name, device, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        orig_call(name, device, *a)
+        e1.record(stream)
+        records.append((name, a, e0, e1))
+
+    import adsorbdiff_b200.painn as painn_mod
+    import adsorbdiff_b200.denoiser as den_mod
+
+    agg = {}
+    for r in range(reps):
+        records.clear()
+        painn_mod.call = timed_call
+        den_mod.call = timed_call
+        try:
+            model._run(plan, z, pos)
+            den_mod.call("adk_se3_step", dev, _cabi.ptr(pos), _cabi.ptr(plan.cell_f32), _cabi.ptr(plan.atom_off),
+                         _cabi.ptr(tags), _cabi.ptr(fixed), _cabi.ptr(plan.out[0]), _cabi.ptr(plan.out[1]),
+                         _cabi.ptr(sched), _cabi.ptr(step), plan.B, _cabi.ptr(max_upd))
+        finally:
+            painn_mod.call = orig_call
+            den_mod.call = orig_call
+        torch.cuda.synchronize(dev)
+        step.zero_()
+        if r == 0:
+            continue  # first instrumented pass is warm-up
+        for name, a, e0, e1 in records:
+            key = name
+            if name == "adk_linear":
+                M, N, K = a[4], a[5], a[6]
+                key = f"adk_linear[{N}x{K}]" if M >= plan.N else key
+            d = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0})
+            d["ms"] += e0.elapsed_time(e1) / (reps - 1)
+            d["launches"] += 1.0 / (reps - 1)
+            if name == "adk_linear":
+                d["flops"] += 2.0 * a[4] * a[5] * a[6] / (reps - 1)
+    return agg
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    from adsorbdiff_b200 import PaiNN, _cabi, synthetic as S
+    from adsorbdiff_b200.denoiser import schedule_table
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = _peaks()
+
+    S_per = args.systems
+    model = PaiNN(None, 0, 1, so3_denoising=True).to(dev).eval()
+    model.load_state_dict(S.random_state_dict(0), strict=True)
+    # 64 distinct systems tiled to S_per (distinct initial placements make every copy different)
+    base = [S.make_system(rank * 100000 + i) for i in range(min(64, S_per))]
+    host = S.collate([base[i % len(base)] for i in range(S_per)])
+    N = int(host.pos.shape[0])
+
+    # host-resident (pinned) inputs for the e2e leg
+    pin = lambda t: t.pin_memory()
+    h_pos = pin(host.pos.clone())
+    batch = host.clone().to(dev)
+    plan, z, pos = model._prepare(batch)
+    tags = batch.tags.to(torch.int32).contiguous()
+    fixed = batch.fixed.to(torch.int32).contiguous()
+    torch.manual_seed(1234 + rank)
+    noise = torch.rand(S_per, 3).to(dev)
+    _cabi.call("adk_init_placement", dev, _cabi.ptr(pos), _cabi.ptr(plan.cell_f32), _cabi.ptr(plan.atom_off),
+               _cabi.ptr(tags), _cabi.ptr(noise), S_per)
+    sched = schedule_table(SAMPLER_PARAMS, dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    max_upd = torch.zeros(S_per, dtype=torch.float32, device=dev)
+
+    def one_step():
+        model._run(plan, z, pos)
+        _cabi.call("adk_se3_step", dev, _cabi.ptr(pos), _cabi.ptr(plan.cell_f32), _cabi.ptr(plan.atom_off),
+                   _cabi.ptr(tags), _cabi.ptr(fixed), _cabi.ptr(plan.out[0]), _cabi.ptr(plan.out[1]),
+                   _cabi.ptr(sched), _cabi.ptr(step), S_per, _cabi.ptr(max_upd))
+
+    # eager warm-up step, status check, then capture one step as a CUDA graph
+    l0 = _cabi.launch_count
+    one_step()
+    launches_per_step = _cabi.launch_count - l0
+    torch.cuda.synchronize(dev)
+    model.check_status(plan)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        one_step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    total_steps = SAMPLER_PARAMS["num_steps"]
+
+    def run_steps(k):
+        for _ in range(k):
+            if int(run_steps.done) % total_steps == 0:
+                step.zero_()  # schedule wraps every 100 steps (a new sampling run)
+            graph.replay()
+            run_steps.done += 1
+
+    run_steps.done = 1  # the eager step above consumed schedule row 0
+    run_steps(max(args.warmup, 3))
+
+    # ---- timed region: K steps, device timed, max over ranks ----------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_steps(args.steps)
+    if world > 1:
+        # the job's only collective: gather final positions of every rank's systems
+        gathered = torch.empty(world * N, 3, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gathered, pos)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * S_per * args.steps / (ms / 1e3)
+    model.check_status(plan)
+
+    # ---- e2e: same steps through host buffers (pinned H2D of inputs, D2H of result, every step) ----
+    h_out = torch.empty(N, 3, dtype=torch.float32).pin_memory()
+    h_pos.copy_(pos.cpu())
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        pos.copy_(h_pos, non_blocking=True)
+        if int(run_steps.done) % total_steps == 0:
+            step.zero_()
+        graph.replay()
+        run_steps.done += 1
+        h_out.copy_(pos, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()  # the caller reads the result before the next step
+        h_pos.copy_(h_out)
+    f1.record()
+    barrier()
+    t2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * S_per * args.steps / (float(t2.item()) / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0, eager, CUDA events) ----
+    step.zero_()
+    agg = kernel_breakdown(model, plan, z, pos, tags, fixed, sched, step, max_upd)
+    total_ms = sum(d["ms"] for d in agg.values())
+    E = int(plan.row_deg.sum().item())
+    F, L = model.hidden_channels, model.num_layers
+    msg_bytes_per_launch = N * 20480.0 * (F / 512.0) + E * 24.0  # fused-design algorithmic bytes
+    kernels = {}
+    for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        ent = {"ms_per_step": round(d["ms"], 4), "share": round(d["ms"] / total_ms, 4), "launches": round(d["launches"])}
+        if k == "adk_message":
+            per = d["ms"] / max(d["launches"], 1)
+            ent["hbm_gbs"] = round(msg_bytes_per_launch / (per * 1e-3) / 1e9, 1)
+            ent["hbm_frac"] = round(ent["hbm_gbs"] / peaks["hbm"], 4)
+        if d["flops"] > 0:
+            ent["tflops"] = round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2)
+        kernels[k] = ent
+    msg = agg.get("adk_message", {"ms": 0.0, "launches": 1})
+    lin_ms = sum(d["ms"] for k, d in agg.items() if k.startswith("adk_linear"))
+    lin_flops = sum(d["flops"] for k, d in agg.items() if k.startswith("adk_linear"))
+    if lin_ms >= msg["ms"]:
+        ach = lin_flops / (lin_ms * 1e-3) / 1e12
+        roofline = {"kernel": "adk_linear (node-wise dense contractions, fp32)", "bound": "tensor",
+                    "achieved": round(ach, 2), "peak": peaks["bf16_sustained"] or peaks["bf16"], "unit": "TFLOP/s",
+                    "frac": round(ach / (peaks["bf16_sustained"] or peaks["bf16"]), 4), "traffic": None,
+                    "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)"}
+    else:
+        per = msg["ms"] / max(msg["launches"], 1)
+        ach = msg_bytes_per_launch / (per * 1e-3) / 1e9
+        roofline = {"kernel": "adk_message (fused rbf + message + CSR reduction)", "bound": "hbm",
+                    "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": round(ach / peaks["hbm"], 4), "traffic": None, "peak_source": peaks["source"]}
+
+    cores = os.cpu_count() or 1
+    cpu_val, cpu_dt = cpu_port_rate(4, 2, cores)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(S_per), "systems_per_gpu": S_per, "atoms_per_gpu": N, "edges_per_gpu": E,
+                   "l2": "inputs larger than L2 (per-step activation working set ~%.1f GB)" % (N * F * 4 * 22 / 1e9),
+                   "cuda_graph": True, "early_stop": False},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * 12, "d2h_bytes_per_step": N * 12},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"4 systems x 2 steps of the same workload in {cpu_dt:.1f} s (oracle port, fp32)"},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--systems", type=int, default=1024, help="systems per GPU")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,174 @@
+/*
+ * adsorbdiff_b200 -- C ABI of the B200-native PaiNN denoising hot path.
+ *
+ * Drop-in boundary for the reference's (pure-Python) PaiNN score-model forward and the
+ * per-step SE(3) update of its reverse-diffusion sampler.  The reference has no FFI of its
+ * own (no native code at all), so each entry point below names the
+ * reference Python function(s) whose arithmetic it replaces (file:line under
+ * /root/reference/adsorbdiff/).  INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked "host";
+ *   - the caller owns every buffer; nothing is allocated, freed or retained by the library;
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*), no internal
+ *     synchronisation, safe to capture into a CUDA graph after adk_init();
+ *   - return value: 0 on success, a negative ADK_E* code on argument errors, or the positive
+ *     cudaError_t of a failed launch.  Data-dependent failures (a system without neighbours,
+ *     an in-degree above the staging capacity) are reported through the device-side `status`
+ *     word (bit mask ADK_STATUS_*), read by the host whenever it chooses to synchronise.
+ *   - node features: x[N][F], vec[N][3][F] (node, xyz, feature), fp32, F = hidden_channels;
+ *     weights in torch.nn.Linear layout [out][in], fp32.
+ */
+#ifndef ADSORBDIFF_B200_H
+#define ADSORBDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADK_ABI_VERSION 1
+
+#define ADK_EINVAL (-22)   /* bad argument (null pointer, unsupported size) */
+#define ADK_ERANGE (-34)   /* size beyond a compiled capacity (images, atoms per system) */
+
+#define ADK_STATUS_EMPTY_SYSTEM 1u  /* a system has zero neighbours: reference raises ValueError
+                                       (models/painn/painn_denoising.py:370-375) */
+#define ADK_STATUS_ROW_OVERFLOW 2u  /* an atom's in-degree exceeds ADK_MAX_ROW_DEGREE */
+
+#define ADK_MAX_IMAGES 2048        /* periodic images enumerated per system */
+#define ADK_MAX_ROW_DEGREE 512     /* in-edges per atom after symmetrisation */
+#define ADK_MAX_ATOMS_PER_SYSTEM 1024
+
+/* activation codes for adk_linear */
+#define ADK_ACT_NONE 0
+#define ADK_ACT_SSILU 1            /* ScaledSiLU: silu(x)/0.6 (models/gemnet_oc/layers/base_layers.py:65-72) */
+
+int adk_abi_version(void);
+
+/* One-time per process and device: opts kernels into their dynamic shared-memory sizes.
+ * Must be called before any launch and outside stream capture. */
+int adk_init(void);
+
+/* Bytes of dynamic shared memory adk_neighbors needs for (n_max atoms, num_images, max_nbrs);
+ * negative ADK_ERANGE if it does not fit one CTA. */
+int64_t adk_neighbors_smem_bytes(int n_max, int num_images, int max_nbrs);
+
+/*
+ * Periodic-boundary neighbour search + per-atom top-k + PBC distances + edge symmetrisation.
+ * Replaces: radius_graph_pbc (utils/utils.py:556-730), get_max_neighbors_mask (utils.py:733-853,
+ * enforce_max_strictly=True, ties broken by enumeration order), get_pbc_distances
+ * (utils.py:513-553), PaiNN.generate_graph_values / symmetrize_edges
+ * (models/painn/painn_denoising.py:353-400, 262-327).
+ *
+ *   pos[N][3], cell[B][3][3] (rows = lattice vectors), atom_off[B+1] (prefix sum of natoms),
+ *   rep[3] = image repeats per lattice direction (host ints; 0 for a non-periodic direction),
+ *   cutoff2 = fp32(radius*radius), max_nbrs = k.
+ * Outputs (in-edge CSR by target atom; system b owns edge slots [2k*atom_off[b], 2k*atom_off[b+1])):
+ *   row_start[N], row_deg[N]  absolute slot of each atom's first in-edge, and its in-degree
+ *   e_src[2kN]                global index of the source atom
+ *   e_geo[2kN][4]             (d, rx, ry, rz): clamped distance and unit vector target->source image
+ *   kept_pack[N][k], kept_cnt[N]  the directed half (j<i rule) in reference order, packed
+ *                             (j_local<<16 | image_index), for adk_export_edges
+ *   sys_counts[B][2]          (raw top-k edge count, kept half count) per system
+ *   status                    ADK_STATUS_* bits are OR-ed in
+ * Rows are ordered by (d, source, image): deterministic, no atomics on floating point.
+ */
+int adk_neighbors(const float* pos, const float* cell, const int32_t* atom_off, int B, int n_max,
+                  const int32_t rep[3] /* host */, float cutoff2, int max_nbrs,
+                  int32_t* row_start, int32_t* row_deg, int32_t* e_src, float* e_geo,
+                  uint32_t* kept_pack, int32_t* kept_cnt, int32_t* sys_counts,
+                  uint32_t* status, void* stream);
+
+/*
+ * Materialise the edge list exactly as PaiNN.generate_graph_values returns it
+ * (painn_denoising.py:394-400): per system [kept..., reversed...], kept ordered by (i, j, image).
+ *   edge_index[2][E_cap] int64 (row 0 = source, row 1 = target), cell_offsets[E_cap][3],
+ *   dist[E_cap], unit_vec[E_cap][3], neighbors[B] int64 (= 2 * kept), sys_edge_off[B+1] scratch.
+ * The number of valid edges is sys_edge_off[B] (device).  Needed for API parity and tests only;
+ * the message kernel consumes the CSR of adk_neighbors directly.
+ */
+int adk_export_edges(const float* pos, const float* cell, const int32_t* atom_off, int B,
+                     const int32_t rep[3] /* host */, int max_nbrs,
+                     const uint32_t* kept_pack, const int32_t* kept_cnt, const int32_t* sys_counts,
+                     int32_t* sys_edge_off, int64_t* edge_index, int64_t e_cap, float* cell_offsets,
+                     float* dist, float* unit_vec, int64_t* neighbors, void* stream);
+
+/* x[n] = emb[z[n]-1] ; vec = 0.  Replaces AtomEmbedding.forward
+ * (models/gemnet_oc/layers/embedding_block.py:35-43) and painn_denoising.py:425-426. */
+int adk_embed(const int64_t* z, const float* emb, int num_elements, int N, int F,
+              float* x, float* vec, void* stream);
+
+/* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5).  Replaces
+ * PaiNNMessage.x_layernorm (painn_denoising.py:517,531). */
+int adk_layernorm(const float* x, const float* gamma, const float* beta, int M, int F, float eps,
+                  float* y, void* stream);
+
+/* C[M][N] = act(A[M][K] . W[N][K]^T + bias[N]); lda/ldc in elements; bias may be NULL.
+ * The dense contractions of PaiNNMessage.x_proj (painn_denoising.py:508-512,531),
+ * PaiNNUpdate.vec_proj/xvec_proj (:580-587,602-613) and GatedEquivariantBlock (:667-676,689-693). */
+int adk_linear(const float* A, int64_t lda, const float* W, const float* bias, int M, int N, int K,
+               int act, float* C, int64_t ldc, void* stream);
+
+/*
+ * Fused edge featurisation + rbf projection + message + segmented reduction + residual.
+ * Replaces RadialBasis.forward (models/gemnet_oc/layers/radial_basis.py:235-244; Gaussian basis
+ * :64-82, polynomial envelope :18-43), PaiNNMessage.rbf_proj/message/aggregate
+ * (painn_denoising.py:534-567) and the residual of PaiNN.forward (:443-445).
+ *   xh[N][3F] (output of x_proj), vec_in[N][3][F] (NULL => all-zero, layer 0),
+ *   w_rbf[3F][R], b_rbf[3F], rbf_offset[R] (Gaussian centres in scaled distance), R = num_rbf
+ *   x_io[N][F]: in = x, out = (x + dx)/sqrt(2);  vec_out[N][3][F] = vec_in + dvec
+ *   (vec_out must not alias vec_in: other rows still read it).
+ */
+int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
+                const float* e_geo, const float* xh, const float* vec_in, const float* w_rbf,
+                const float* b_rbf, const float* rbf_offset, int N, int F, int R, float cutoff,
+                int envelope_exponent, float* x_io, float* vec_out, void* stream);
+
+/* From vp[N][3][2F] = vec_proj(vec) = (vec1|vec2): dot[N][F] = sum_xyz vec1*vec2 / sqrt(F),
+ * cat[N][2F] = [x | sqrt(sum_xyz vec2^2 + 1e-8)].  PaiNNUpdate.forward (painn_denoising.py:602-613). */
+int adk_update_prep(const float* x, const float* vp, int N, int F, float* dot, float* cat, void* stream);
+
+/* h[N][3F] = (a|b|c): x = (x + (a + b*dot)/sqrt(2)) * scale ; vec += c * vec1 (vec1 = vp[:, :, :F]).
+ * PaiNNUpdate.forward (:614-623), PaiNN.forward (:449-451), ScaleFactor.forward
+ * (modules/scaling/scale_factor.py:157-172; scale == 0 means "not fitted": no multiply). */
+int adk_update_gate(const float* h, const float* dot, const float* vp, const float* scale /* device scalar */,
+                    int N, int F, float* x, float* vec, void* stream);
+
+/* GatedEquivariantBlock (painn_denoising.py:688-697), the parts around its linears:
+ * prep: cat[N][2C] = [x | ||v1p||_xyz] from v1p[N][3][C] = vec1_proj(v);
+ * gate: from u[N][2*Co] = (s|g): x_out[N][Co] = ssilu(s), v_out[N][3][Co] = g * v2p (v2p = vec2_proj(v)). */
+int adk_head_prep(const float* x, const float* v1p, int N, int C, float* cat, void* stream);
+int adk_head_gate(const float* u, const float* v2p, int N, int Co, float* x_out, float* v_out, void* stream);
+
+/*
+ * Initial placement: random in-plane centre of mass for the adsorbate (tags == 2), z kept.
+ * Replaces Denoiser.reverse_sde_sampling_rot lines denoising_torch.py:215-232.
+ * noise[B][3] = the torch.rand(B,3) draw.  pos is updated in place.
+ */
+int adk_init_placement(float* pos, const float* cell, const int32_t* atom_off, const int32_t* tags,
+                       const float* noise, int B, void* stream);
+
+/*
+ * One reverse-diffusion ODE step on the rigid adsorbate of every system.
+ * Replaces DiffTorchCalc.get_denoising_prediction (denoising_torch.py:491-500), _get_ads_output
+ * (:460-467), the update / PBC wrap / rigid rotation of reverse_sde_sampling_rot (:266-353) and
+ * axis_angle_to_matrix (utils/rot_utils.py:18-98).
+ *   score_tr/score_rot[N][3] = the two model outputs.
+ *   sched[S][3] = per-step scalars (c_tr = 0.5*tr_g^2*dt, dt, rot_g2 = fp32(rot_g^2)); the row used is
+ *   sched[*step], and *step (a device counter) is incremented afterwards, so a captured CUDA graph
+ *   can be replayed for all S steps without host-side parameter updates.
+ *   delta COM = c_tr * mean_tr (z zeroed), wrapped into the cell; rotation vector =
+ *   ((0.5*mean_rot)*dt)*rot_g2.  pos updated in place; max_abs_upd[B] = max |delta COM| per system
+ *   (for the reference's allclose early-stop, :312-320).
+ */
+int adk_se3_step(float* pos, const float* cell, const int32_t* atom_off, const int32_t* tags,
+                 const int32_t* fixed, const float* score_tr, const float* score_rot,
+                 const float* sched, int32_t* step, int B, float* max_abs_upd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADSORBDIFF_B200_H */
