@@ -127,6 +127,8 @@ def main():
 
     b = sampler_batch()
     ns.utils.radius_graph_pbc.__defaults__[-1][:] = [True, True, True]
+    # tamed output scale: see synthetic.random_state_dict(score_scale=...)
+    model.load_state_dict(S.random_state_dict(0, score_scale=S.SAMPLER_SCORE_SCALE), strict=True)
     calc = ns.DiffTorchCalc(_FakeTrainer(model))
     den = ns.Denoiser(b, calc, dict(SAMPLER_PARAMS), device="cpu", traj_dir=None, traj_names=b.sid)
     import ase.io  # the inert shim

@@ -38,3 +38,10 @@ def weights():
     from adsorbdiff_b200 import synthetic as S
 
     return S.random_state_dict(0)
+
+
+@pytest.fixture(scope="session")
+def sampler_weights():
+    from adsorbdiff_b200 import synthetic as S
+
+    return S.random_state_dict(0, score_scale=S.SAMPLER_SCORE_SCALE)

@@ -76,7 +76,8 @@ def test_forward_matches_reference(name, golden, weights):
             assert np.abs(tr[k][rows].numpy() - ref).max() <= 2e-6 * np.abs(ref).max(), k
 
 
-def test_sampler_matches_reference(golden, weights):
+def test_sampler_matches_reference(golden, sampler_weights):
+    weights = sampler_weights
     g = golden("sampler")
     params = ast.literal_eval(str(g["params"]))
     b = sampler_batch()
