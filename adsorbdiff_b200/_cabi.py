@@ -17,6 +17,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 ABI_VERSION = 1
 STATUS_EMPTY_SYSTEM = 1
 STATUS_ROW_OVERFLOW = 2
+STATUS_F16_OVERFLOW = 4
 MAX_IMAGES = 2048
 MAX_ATOMS_PER_SYSTEM = 1024
 ACT_NONE, ACT_SSILU = 0, 1
@@ -34,8 +35,11 @@ SIGNATURES = {
     "adk_embed": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "adk_layernorm": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P]),
     "adk_linear": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int, c_int, _P, c_int64, _P]),
+    "adk_split_f16": (c_int, [_P, c_int64, c_int, c_int, c_float, _P, c_int64, _P, _P]),
+    "adk_linear_tc": (c_int, [_P, c_int64, c_int, _P, c_int, c_int, _P, c_float, c_int, _P, c_int64,
+                              _P, c_int64, c_float, _P, _P]),
     "adk_message": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int,
-                            _P, _P, _P]),
+                            _P, _P, _P, c_int, c_int, _P]),
     "adk_update_prep": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "adk_update_gate": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
     "adk_head_prep": (c_int, [_P, _P, c_int, c_int, _P, _P]),
@@ -54,7 +58,7 @@ _inited_devices: set[int] = set()
 launch_count = 0  # kernels launched through this binding (bench.py reports it)
 
 _LAUNCHES = {  # kernels behind one entry-point call
-    "adk_neighbors": 1, "adk_export_edges": 2, "adk_embed": 1, "adk_layernorm": 1, "adk_linear": 1,
+    "adk_neighbors": 1, "adk_export_edges": 2, "adk_embed": 1, "adk_layernorm": 1, "adk_linear": 1, "adk_split_f16": 1, "adk_linear_tc": 1,
     "adk_message": 1, "adk_update_prep": 1, "adk_update_gate": 1, "adk_head_prep": 1, "adk_head_gate": 1,
     "adk_init_placement": 1, "adk_se3_step": 2,
 }

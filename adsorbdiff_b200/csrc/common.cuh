@@ -34,6 +34,16 @@ __device__ __forceinline__ float ssilu(float x) {
     return (x / (1.0f + expf(-x))) * (1.0f / 0.6f);
 }
 
+// packed fp32x2 FMA (Blackwell FFMA2): d = a * b + c on both halves, one issue slot
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace adk
@@ -42,3 +52,4 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 int adk_neighbors_set_attrs();
 int adk_message_set_attrs();
 int adk_linear_set_attrs();
+int adk_linear_tc_set_attrs();

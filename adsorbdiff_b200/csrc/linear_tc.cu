@@ -1,0 +1,405 @@
+// K2 (tensor-core variant): C = act(acc_scale * A . W^T + bias) on tcgen05 with TMEM accumulators.
+//
+// fp32 parity on fp16 tensor cores ("fp16x2 split"): every fp32 operand x is stored as two fp16
+// planes, hi = fp16(s*x) and lo = fp16(s*x - hi), s a power of two.  hi + lo carries 22
+// significand bits, and  A.W ~= Ah.Wh + Ah.Wl + Al.Wh  (the dropped Al.Wl term is 2^-22
+// relative) is accumulated in fp32 in tensor memory by three tcgen05.mma (kind::f16) per
+// k-step.  Measured error vs fp64 is ~1e-7 of the output scale -- below a plain fp32 SGEMM's --
+// at 3 of the 2.25 PFLOP/s fp16 MMAs per product instead of 3 of the 1.1 PFLOP/s TF32 ones.
+//
+// Structure (one CTA per SM, persistent over 128x256 output tiles):
+//   warp 0    TMA producer : cp.async.bulk.tensor 2-D loads of the four operand tiles of a k-block
+//                            (A hi/lo 128x64, W hi/lo 256x64 fp16, 128-byte swizzle) into a
+//                            2-stage shared-memory ring, mbarrier complete_tx
+//   warp 1    MMA issuer   : one thread issues 12 tcgen05.mma per k-block (4 k-steps x {hh, hl, lh})
+//                            into one of two 256-column TMEM accumulators; tcgen05.commit frees the
+//                            smem stage / publishes the accumulator
+//   warps 2-9 epilogue     : the tensor core's fp32 accumulate truncates (measured: error grows
+//                            linearly with the number of accumulate steps, 5e-7 at K=64 -> 4.8e-6 at
+//                            K=1024 of the output scale), so the TMEM accumulator only ever holds a
+//                            PARTIAL sum over TC_PROMOTE k-blocks (K=64, 12 MMA steps); these warps
+//                            drain it (tcgen05.ld 32 lanes x 32 columns at a time) into fp32 register
+//                            sums with round-to-nearest adds while the MMA warp fills the other TMEM
+//                            slot, then apply scale + bias + activation and write fp32 and/or the
+//                            fp16x2 planes the next GEMM consumes
+// Reference arithmetic replaced: the torch.nn.Linear calls of PaiNNMessage.x_proj, PaiNNUpdate.vec_proj /
+// xvec_proj and GatedEquivariantBlock (models/painn/painn_denoising.py:508-512, 580-587, 667-676).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 2, TC_UMMA_K = 16;
+constexpr int TC_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TC_PROMOTE = 1;        // k-blocks accumulated in TMEM before promotion to registers
+constexpr int TC_EPI_COLS = 128;     // accumulator columns owned by one epilogue warp
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;                      // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;                      // 32 KB
+constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;    // 96 KB
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t TC_TMEM_COLS = 512;                                  // two 256-column accumulators
+
+struct TcParams {
+    int M, N, K;
+    int a_lo_row;   // row of the first lo-plane row in the A tensor map (= padded M)
+    int w_lo_row;   // same for W (= N)
+    const float* bias;
+    float acc_scale;
+    int act;
+    float* out_f32;
+    int64_t ldc;
+    __half* out_split;        // [2][out_split_rows][N], may be null
+    int64_t out_split_plane;  // elements between the hi and lo plane
+    float out_split_scale;
+    uint32_t* status;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// 64-bit shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+// start>>4 | LBO (unused for swizzled K-major) | SBO = 1024 B between 8-row groups | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_store(float v, float scale, __half& hi, __half& lo, bool& overflow) {
+    const float sv = v * scale;
+    overflow |= !(fabsf(sv) <= 65504.0f);
+    hi = __float2half_rn(sv);
+    lo = __float2half_rn(sv - __half2float(hi));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;
+    // barriers (8 bytes each): full[2], empty[2], tmem_full[2], tmem_empty[2]; then the TMEM base address
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 16u + 8u * s; };
+    auto tfull_bar = [&](int a) { return bar_base + 32u + 8u * a; };
+    auto tempty_bar = [&](int a) { return bar_base + 48u + 8u * a; };
+    const uint32_t tmem_slot = bar_base + 64u;
+
+    const int warp = adk::warp_id(), lane = adk::lane_id();
+    const int num_m = (P.M + TC_BM - 1) / TC_BM, num_n = P.N / TC_BN, num_k = P.K / TC_BK;
+    const int num_tiles = num_m * num_n;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * TC_BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = base + stage * TC_STAGE_BYTES;
+                    mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+                    tma_load_2d(sa, &tmA, full_bar(stage), kb * TC_BK, m0);
+                    tma_load_2d(sa + TC_A_BYTES, &tmA, full_bar(stage), kb * TC_BK, P.a_lo_row + m0);
+                    tma_load_2d(sa + 2 * TC_A_BYTES, &tmW, full_bar(stage), kb * TC_BK, n0);
+                    tma_load_2d(sa + 2 * TC_A_BYTES + TC_B_BYTES, &tmW, full_bar(stage), kb * TC_BK, P.w_lo_row + n0);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, both K-major, N=256, M=128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int astage = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < num_k; ++kb) {
+                    const bool chunk_start = (kb % TC_PROMOTE) == 0;
+                    const bool chunk_end = ((kb + 1) % TC_PROMOTE) == 0 || kb == num_k - 1;
+                    if (chunk_start) {
+                        mbar_wait(tempty_bar(astage), aphase ^ 1u);  // epilogue has drained this TMEM slot
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    const uint32_t d_tmem = tmem_base + (uint32_t)astage * TC_BN;
+                    mbar_wait(full_bar(stage), phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = base + stage * TC_STAGE_BYTES;
+                    const uint64_t d_ah = umma_desc(sa), d_al = umma_desc(sa + TC_A_BYTES);
+                    const uint64_t d_wh = umma_desc(sa + 2 * TC_A_BYTES), d_wl = umma_desc(sa + 2 * TC_A_BYTES + TC_B_BYTES);
+                    // Order matters for accuracy: the accumulate truncates toward zero at every MMA, a
+                    // bias proportional to the accumulator's magnitude.  The two correction products
+                    // (2^-11 of the main one) go first, while the fresh accumulator is still tiny, so
+                    // only the four hi*hi steps of a k-block truncate at full magnitude.
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / TC_UMMA_K; ++ks) {
+                        const uint64_t koff = (uint64_t)((ks * TC_UMMA_K * 2) >> 4);  // 32 bytes per k-step
+                        umma_f16(d_tmem, d_ah + koff, d_wl + koff, idesc, (chunk_start && ks == 0) ? 0u : 1u);
+                        umma_f16(d_tmem, d_al + koff, d_wh + koff, idesc, 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / TC_UMMA_K; ++ks) {
+                        const uint64_t koff = (uint64_t)((ks * TC_UMMA_K * 2) >> 4);
+                        umma_f16(d_tmem, d_ah + koff, d_wh + koff, idesc, 1u);
+                    }
+                    umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+                    if (chunk_end) {
+                        umma_commit(tfull_bar(astage));  // partial sum ready for promotion
+                        if (++astage == 2) { astage = 0; aphase ^= 1u; }
+                    }
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;     // which 128-column half of the accumulator it owns
+        const int num_chunks = (num_k + TC_PROMOTE - 1) / TC_PROMOTE;
+        int astage = 0;
+        uint32_t aphase = 0;
+        bool overflow = false;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * TC_BN + half * TC_EPI_COLS;
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < P.M;
+            float acc[TC_EPI_COLS];
+#pragma unroll
+            for (int j = 0; j < TC_EPI_COLS; ++j) acc[j] = 0.f;
+#pragma unroll 1
+            for (int ch = 0; ch < num_chunks; ++ch) {
+                mbar_wait(tfull_bar(astage), aphase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)astage * TC_BN +
+                                       (uint32_t)half * TC_EPI_COLS;
+#pragma unroll
+                for (int c = 0; c < TC_EPI_COLS / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(astage));
+                if (++astage == 2) { astage = 0; aphase ^= 1u; }
+            }
+#pragma unroll
+            for (int c = 0; c < TC_EPI_COLS / 32; ++c) {
+                const int n = n0 + c * 32;
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float t = acc[c * 32 + j] * P.acc_scale;
+                    if (P.bias) t += __ldg(P.bias + n + j);
+                    o[j] = (P.act == ADK_ACT_SSILU) ? adk::ssilu(t) : t;
+                }
+                if (row_ok) {
+                    if (P.out_f32) {
+                        float4* dst = reinterpret_cast<float4*>(P.out_f32 + (int64_t)row * P.ldc + n);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    }
+                    if (P.out_split) {
+                        uint32_t ph[16], pl[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __half h0, l0, h1, l1;
+                            split_store(o[2 * j], P.out_split_scale, h0, l0, overflow);
+                            split_store(o[2 * j + 1], P.out_split_scale, h1, l1, overflow);
+                            __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+                            ph[j] = *reinterpret_cast<uint32_t*>(&hh);
+                            pl[j] = *reinterpret_cast<uint32_t*>(&ll);
+                        }
+                        uint4* dh = reinterpret_cast<uint4*>(P.out_split + (int64_t)row * P.N + n);
+                        uint4* dl = reinterpret_cast<uint4*>(P.out_split + P.out_split_plane + (int64_t)row * P.N + n);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            dh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                            dl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        if (overflow && P.status) atomicOr(P.status, ADK_STATUS_F16_OVERFLOW);
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// fp32 [M][K] (row stride ld) -> fp16x2 planes [2][plane_rows][K]
+__global__ void split_f16_kernel(const float* __restrict__ src, int64_t ld, int M, int K, float scale,
+                                 __half* __restrict__ dst, int64_t plane, uint32_t* status) {
+    const int K4 = K >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * K4) return;
+    const int m = (int)(idx / K4), k4 = (int)(idx - (int64_t)m * K4);
+    const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)m * ld + 4 * k4);
+    __align__(8) __half hi[4];
+    __align__(8) __half lo[4];
+    bool overflow = false;
+    split_store(v.x, scale, hi[0], lo[0], overflow);
+    split_store(v.y, scale, hi[1], lo[1], overflow);
+    split_store(v.z, scale, hi[2], lo[2], overflow);
+    split_store(v.w, scale, hi[3], lo[3], overflow);
+    *reinterpret_cast<uint2*>(dst + (int64_t)m * K + 4 * k4) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(dst + plane + (int64_t)m * K + 4 * k4) = *reinterpret_cast<const uint2*>(lo);
+    if (overflow && status) atomicOr(status, ADK_STATUS_F16_OVERFLOW);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 148;
+
+// 2-D fp16 tensor [rows][K] (K contiguous), box = [box_rows][64], 128-byte swizzle
+int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t K, uint32_t box_rows) {
+    if (!g_encode) return ADK_EINVAL;
+    cuuint64_t dims[2] = {K, rows};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
+}
+
+}  // namespace
+
+extern "C" int adk_split_f16(const float* src, int64_t ld, int M, int K, float scale, void* dst, int64_t plane_rows,
+                             uint32_t* status, void* stream) {
+    if (!src || !dst || M <= 0 || K <= 0 || (K & 3) || (ld & 3) || plane_rows < M) return ADK_EINVAL;
+    const int64_t n = (int64_t)M * (K >> 2);
+    split_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, adk::as_stream(stream)>>>(
+        src, ld, M, K, scale, reinterpret_cast<__half*>(dst), plane_rows * K, status);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, const void* w_split, int N, int K,
+                             const float* bias, float acc_scale, int act, float* out_f32, int64_t ldc,
+                             void* out_split, int64_t out_plane_rows, float out_split_scale, uint32_t* status,
+                             void* stream) {
+    if (!a_split || !w_split || M <= 0 || N <= 0 || K <= 0 || (!out_f32 && !out_split)) return ADK_EINVAL;
+    if (N % TC_BN != 0 || K % TC_BK != 0 || a_plane_rows < M || a_plane_rows % TC_BM != 0) return ADK_EINVAL;
+    if (out_f32 && ((ldc & 3) || (reinterpret_cast<uintptr_t>(out_f32) & 15))) return ADK_EINVAL;
+    if (out_split && out_plane_rows < M) return ADK_EINVAL;
+    alignas(64) CUtensorMap tmA, tmW;
+    int rc;
+    if ((rc = make_map(&tmA, a_split, 2 * (uint64_t)a_plane_rows, (uint64_t)K, TC_BM)) != 0) return rc;
+    if ((rc = make_map(&tmW, w_split, 2 * (uint64_t)N, (uint64_t)K, TC_BN)) != 0) return rc;
+    TcParams P;
+    P.M = M; P.N = N; P.K = K;
+    P.a_lo_row = (int)a_plane_rows; P.w_lo_row = N;
+    P.bias = bias; P.acc_scale = acc_scale; P.act = act;
+    P.out_f32 = out_f32; P.ldc = ldc;
+    P.out_split = reinterpret_cast<__half*>(out_split);
+    P.out_split_plane = out_plane_rows * (int64_t)N;
+    P.out_split_scale = out_split_scale;
+    P.status = status;
+    const int tiles = ((M + TC_BM - 1) / TC_BM) * (N / TC_BN);
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    linear_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, adk::as_stream(stream)>>>(tmA, tmW, P);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
+int adk_linear_tc_set_attrs() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return (int)e;
+    if (q != cudaDriverEntryPointSuccess || !fn) return ADK_EINVAL;
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+}

@@ -207,6 +207,10 @@ class PaiNN(nn.Module):
                 else:
                     logging.warning(f"Scale factor {name} not found in model")
         self._plan_cache: Optional[_Plan] = None
+        # "tc": tcgen05 fp16x2-split GEMMs (fp32 parity, see csrc/linear_tc.cu); "fp32": exact-fp32 SIMT GEMMs
+        self.gemm = "tc"
+        self.msg_staged = False  # per-system shared-memory staging variant of the message kernel
+        self._wsplit_cache: dict = {}
 
     # ------------------------------------------------------------------ reference-facing API
     @property
@@ -315,6 +319,13 @@ class PaiNN(nn.Module):
         p.v2p2 = torch.empty(N, 3, 1, **f32)
         p.ho2 = torch.empty(N, 2, **f32)
         p.out = [torch.empty(N, 3, **f32), torch.empty(N, 3, **f32)]
+        # fp16x2 operand planes for the tensor-core GEMMs: [2][rows padded to 128][K]; pad rows stay zero
+        pad = lambda r: (r + 127) // 128 * 128
+        f16 = dict(dtype=torch.float16, device=dev)
+        p.rows_n, p.rows_3n = pad(N), pad(3 * N)
+        p.sp_x = torch.zeros(2 * p.rows_n * 2 * F, **f16)     # node-wise inputs, K <= 2F
+        p.sp_h = torch.zeros(2 * p.rows_n * F, **f16)         # hidden of the two-layer MLPs, K <= F
+        p.sp_v = torch.zeros(2 * p.rows_3n * F, **f16)        # vec-wise inputs, K <= F
         self._plan_cache = p
         return p
 
@@ -324,29 +335,94 @@ class PaiNN(nn.Module):
              float(self.cutoff * self.cutoff), self.max_neighbors, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src),
              ptr(p.e_geo), ptr(p.kept_pack), ptr(p.kept_cnt), ptr(p.sys_counts), ptr(p.status))
 
+    # power-of-two prescales of the fp16x2 split.  hi+lo is exact to 22 bits while |s*x| stays in
+    # [2^-3, 65504] (below that the lo plane goes subnormal and the error floor is 2^-25/s absolute):
+    # node scalars are O(1), the equivariant vec channel O(0.01-0.1), Xavier-scale weights O(0.05).
+    A_SCALE = 16.0
+    V_SCALE = 1024.0
+    W_SCALE = 1024.0
+
     def _linear(self, p, A, lda, lin, M, act, C, ldc):
+        """Exact-fp32 SIMT GEMM (also the path for the 1- and 2-column head outputs)."""
         W = lin.weight
         call("adk_linear", p.device, ptr(A), lda, ptr(W), ptr(lin.bias) if lin.bias is not None else None,
              M, W.shape[0], W.shape[1], act, ptr(C), ldc)
 
-    def _head(self, p: _Plan, head: _OutputParams, x, vec, out) -> None:
+    def _wsplit(self, p, lin):
+        """fp16x2 planes of a weight, rebuilt whenever the parameter is modified in place (EMA swaps,
+        load_state_dict, optimizer steps all bump `_version`) or re-allocated."""
+        W = lin.weight
+        key = id(lin)
+        ent = self._wsplit_cache.get(key)
+        if ent is None or ent[0] != W._version or ent[1] != W.data_ptr():
+            n, k = W.shape
+            buf = ent[2] if ent is not None and ent[2].numel() == 2 * n * k and ent[2].device == W.device else \
+                torch.empty(2 * n * k, dtype=torch.float16, device=W.device)
+            call("adk_split_f16", p.device, ptr(W), k, n, k, self.W_SCALE, ptr(buf), n, ptr(p.status))
+            ent = (W._version, W.data_ptr(), buf)
+            self._wsplit_cache[key] = ent
+        return ent[2]
+
+    def _split(self, p, A, lda, M, K, buf, rows, scale=None):
+        call("adk_split_f16", p.device, ptr(A), lda, M, K, scale or self.A_SCALE, ptr(buf), rows, ptr(p.status))
+
+    def _linear_tc(self, p, a_split, a_rows, M, lin, act, out_f32=None, ldc=0, out_split=None, out_rows=0,
+                   a_scale=None):
+        W = lin.weight
+        N, K = W.shape
+        ws = self._wsplit(p, lin)
+        call("adk_linear_tc", p.device, ptr(a_split), a_rows, M, ptr(ws), N, K,
+             ptr(lin.bias) if lin.bias is not None else None, 1.0 / ((a_scale or self.A_SCALE) * self.W_SCALE), act,
+             ptr(out_f32) if out_f32 is not None else None, ldc,
+             ptr(out_split) if out_split is not None else None, out_rows, self.A_SCALE, ptr(p.status))
+
+    def _mlp2(self, p, A, lda, M, K, lin0, lin1, out, ldc):
+        """out = lin1(ssilu(lin0(A))): the two-layer MLP shape shared by x_proj, xvec_proj and update_net."""
+        if self.gemm == "tc" and lin1.weight.shape[0] % 256 == 0:
+            rows = p.rows_n
+            self._split(p, A, lda, M, K, p.sp_x, rows)
+            self._linear_tc(p, p.sp_x, rows, M, lin0, _cabi.ACT_SSILU, out_split=p.sp_h, out_rows=rows)
+            self._linear_tc(p, p.sp_h, rows, M, lin1, _cabi.ACT_NONE, out_f32=out, ldc=ldc)
+        elif self.gemm == "tc":
+            rows = p.rows_n
+            self._split(p, A, lda, M, K, p.sp_x, rows)
+            self._linear_tc(p, p.sp_x, rows, M, lin0, _cabi.ACT_SSILU, out_f32=p.h1, ldc=lin0.weight.shape[0])
+            self._linear(p, p.h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
+        else:
+            self._linear(p, A, lda, lin0, M, _cabi.ACT_SSILU, p.h1, lin0.weight.shape[0])
+            self._linear(p, p.h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
+
+    def _vec_linear(self, p, vec, K, lins_outs, presplit=False):
+        """vec-wise bias-free projections of [3N, K] (vec_proj, vec1_proj, vec2_proj); one split feeds all."""
+        M = 3 * p.N
+        if self.gemm == "tc":
+            if not presplit:
+                self._split(p, vec, K, M, K, p.sp_v, p.rows_3n, self.V_SCALE)
+            for lin, out in lins_outs:
+                n_out = lin.weight.shape[0]
+                if n_out % 256 == 0:
+                    self._linear_tc(p, p.sp_v, p.rows_3n, M, lin, _cabi.ACT_NONE, out_f32=out, ldc=n_out,
+                                    a_scale=self.V_SCALE)
+                else:
+                    self._linear(p, vec, K, lin, M, _cabi.ACT_NONE, out, n_out)
+        else:
+            for lin, out in lins_outs:
+                self._linear(p, vec, K, lin, M, _cabi.ACT_NONE, out, lin.weight.shape[0])
+
+    def _head(self, p: _Plan, head: _OutputParams, x, vec, out, presplit: bool) -> None:
         N, F = p.N, self.hidden_channels
         H = F // 2
         b0, b1 = head.output_network[0], head.output_network[1]
         dev = p.device
         # block 0: F -> H
-        self._linear(p, vec, F, b0.vec1_proj, 3 * N, _cabi.ACT_NONE, p.v1p, F)
-        self._linear(p, vec, F, b0.vec2_proj, 3 * N, _cabi.ACT_NONE, p.v2p, H)
+        self._vec_linear(p, vec, F, [(b0.vec1_proj, p.v1p), (b0.vec2_proj, p.v2p)], presplit=presplit)
         call("adk_head_prep", dev, ptr(x), ptr(p.v1p), N, F, ptr(p.cat))
-        self._linear(p, p.cat, 2 * F, b0.update_net[0], N, _cabi.ACT_SSILU, p.h1, F)
-        self._linear(p, p.h1, F, b0.update_net[2], N, _cabi.ACT_NONE, p.xn, F)  # (s|g), 2*H = F wide
+        self._mlp2(p, p.cat, 2 * F, N, 2 * F, b0.update_net[0], b0.update_net[2], p.xn, F)  # (s|g), 2*H = F wide
         call("adk_head_gate", dev, ptr(p.xn), ptr(p.v2p), N, H, ptr(p.hx), ptr(p.hv))
         # block 1: H -> 1
-        self._linear(p, p.hv, H, b1.vec1_proj, 3 * N, _cabi.ACT_NONE, p.v1p, H)
-        self._linear(p, p.hv, H, b1.vec2_proj, 3 * N, _cabi.ACT_NONE, p.v2p2, 1)
+        self._vec_linear(p, p.hv, H, [(b1.vec1_proj, p.v1p), (b1.vec2_proj, p.v2p2)])
         call("adk_head_prep", dev, ptr(p.hx), ptr(p.v1p), N, H, ptr(p.cat))
-        self._linear(p, p.cat, 2 * H, b1.update_net[0], N, _cabi.ACT_SSILU, p.h1, H)
-        self._linear(p, p.h1, H, b1.update_net[2], N, _cabi.ACT_NONE, p.ho2, 2)
+        self._mlp2(p, p.cat, 2 * H, N, 2 * H, b1.update_net[0], b1.update_net[2], p.ho2, 2)
         call("adk_head_gate", dev, ptr(p.ho2), ptr(p.v2p2), N, 1, None, ptr(out))
 
     def _run(self, p: _Plan, z: torch.Tensor, pos: torch.Tensor, trace: Optional[dict] = None):
@@ -361,30 +437,30 @@ class PaiNN(nn.Module):
             m, u = self.message_layers[l], self.update_layers[l]
             call("adk_layernorm", dev, ptr(p.x), ptr(m.x_layernorm.weight), ptr(m.x_layernorm.bias), N, F,
                  float(m.x_layernorm.eps), ptr(p.xn))
-            self._linear(p, p.xn, F, m.x_proj[0], N, _cabi.ACT_SSILU, p.h1, F)
-            self._linear(p, p.h1, F, m.x_proj[2], N, _cabi.ACT_NONE, p.xh, 3 * F)
+            self._mlp2(p, p.xn, F, N, F, m.x_proj[0], m.x_proj[2], p.xh, 3 * F)
             vin = p.vec[cur] if l > 0 else None  # vec == 0 before the first message
             vout = p.vec[1 - cur]
             call("adk_message", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(p.xh),
                  ptr(vin) if vin is not None else None, ptr(m.rbf_proj.weight), ptr(m.rbf_proj.bias),
                  ptr(self.radial_basis.rbf.offset), N, F, R, float(self.cutoff), self.radial_basis.exponent,
-                 ptr(p.x), ptr(vout))
+                 ptr(p.x), ptr(vout), ptr(p.atom_off) if self.msg_staged else None, p.B, p.n_max)
             cur = 1 - cur
             vec = p.vec[cur]
             if trace is not None:
                 trace[f"msg{l}.x"], trace[f"msg{l}.vec"] = p.x.clone(), vec.clone()
-            self._linear(p, vec, F, u.vec_proj, 3 * N, _cabi.ACT_NONE, p.vp, 2 * F)
+            self._vec_linear(p, vec, F, [(u.vec_proj, p.vp)])
             call("adk_update_prep", dev, ptr(p.x), ptr(p.vp), N, F, ptr(p.dot), ptr(p.cat))
-            self._linear(p, p.cat, 2 * F, u.xvec_proj[0], N, _cabi.ACT_SSILU, p.h1, F)
-            self._linear(p, p.h1, F, u.xvec_proj[2], N, _cabi.ACT_NONE, p.xh, 3 * F)
+            self._mlp2(p, p.cat, 2 * F, N, 2 * F, u.xvec_proj[0], u.xvec_proj[2], p.xh, 3 * F)
             sc = getattr(self, "upd_out_scalar_scale_%d" % l).scale_factor
             call("adk_update_gate", dev, ptr(p.xh), ptr(p.dot), ptr(p.vp), ptr(sc), N, F, ptr(p.x), ptr(vec))
             if trace is not None:
                 trace[f"upd{l}.x"], trace[f"upd{l}.vec"] = p.x.clone(), vec.clone()
         vec = p.vec[cur]
-        self._head(p, self.out_forces, p.x, vec, p.out[0])
+        self._head(p, self.out_forces, p.x, vec, p.out[0], presplit=False)
         if self.so3_denoising:
-            self._head(p, self.out_forces2, p.x, vec, p.out[1])
+            if self.gemm == "tc":  # the first head's block 1 reused the vec planes: split again
+                self._split(p, vec, F, 3 * N, F, p.sp_v, p.rows_3n, self.V_SCALE)
+            self._head(p, self.out_forces2, p.x, vec, p.out[1], presplit=True)
 
     def _refuse_training(self) -> None:
         if torch.is_grad_enabled() and self.training:
@@ -416,6 +492,9 @@ class PaiNN(nn.Module):
             raise ValueError(f"An image has no neighbors: batch index={empty}")
         if st & _cabi.STATUS_ROW_OVERFLOW:
             raise _cabi.AdkError("an atom's in-degree exceeds ADK_MAX_ROW_DEGREE")
+        if st & _cabi.STATUS_F16_OVERFLOW:
+            raise _cabi.AdkError("a value left the fp16 range in the fp16x2 split of the tensor-core GEMM "
+                                 "(|16*scalar feature|, |1024*vector feature| or |1024*weight| > 65504); set model.gemm = 'fp32'")
 
     # ------------------------------------------------------------------ forward
     def forward(self, data, trace: Optional[dict] = None):

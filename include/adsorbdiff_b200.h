@@ -38,6 +38,8 @@ extern "C" {
                                        (models/painn/painn_denoising.py:370-375) */
 #define ADK_STATUS_ROW_OVERFLOW 2u  /* an atom's in-degree exceeds ADK_MAX_ROW_DEGREE */
 
+#define ADK_STATUS_F16_OVERFLOW 4u  /* a value left the fp16 range while being split for the tensor-core GEMM */
+
 #define ADK_MAX_IMAGES 2048        /* periodic images enumerated per system */
 #define ADK_MAX_ROW_DEGREE 512     /* in-edges per atom after symmetrisation */
 #define ADK_MAX_ATOMS_PER_SYSTEM 1024
@@ -113,6 +115,26 @@ int adk_linear(const float* A, int64_t lda, const float* W, const float* bias, i
                int act, float* C, int64_t ldc, void* stream);
 
 /*
+ * Tensor-core variant of adk_linear (tcgen05.mma kind::f16, TMEM accumulators, TMA operand loads),
+ * fp32-parity through the "fp16x2 split": an fp32 operand x is held as two fp16 planes
+ * hi = fp16(s*x), lo = fp16(s*x - hi) (s a power of two), and A.W^T is accumulated in fp32 as
+ * Ah.Wh + Ah.Wl + Al.Wh.  Error vs fp64 ~1e-7 of the output scale (tests/test_gpu_linear_tc.py).
+ *
+ * adk_split_f16: src fp32 [M][K] (row stride ld) -> dst fp16 [2][plane_rows][K]; rows >= M untouched.
+ *   ADK_STATUS_F16_OVERFLOW is OR-ed into *status if |s*x| > 65504.
+ * adk_linear_tc: C = act(acc_scale * A.W^T + bias), A = a_split [2][a_plane_rows][K] (a_plane_rows a
+ *   multiple of 128, >= M), W = w_split [2][N][K]; N % 256 == 0, K % 64 == 0; acc_scale = 1/(s_A*s_W).
+ *   Outputs: out_f32 [M][ldc] and/or out_split [2][out_plane_rows][N] (scaled by out_split_scale),
+ *   either may be NULL (not both).
+ */
+int adk_split_f16(const float* src, int64_t ld, int M, int K, float scale, void* dst, int64_t plane_rows,
+                  uint32_t* status, void* stream);
+int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, const void* w_split, int N, int K,
+                  const float* bias, float acc_scale, int act, float* out_f32, int64_t ldc,
+                  void* out_split, int64_t out_plane_rows, float out_split_scale, uint32_t* status,
+                  void* stream);
+
+/*
  * Fused edge featurisation + rbf projection + message + segmented reduction + residual.
  * Replaces RadialBasis.forward (models/gemnet_oc/layers/radial_basis.py:235-244; Gaussian basis
  * :64-82, polynomial envelope :18-43), PaiNNMessage.rbf_proj/message/aggregate
@@ -121,11 +143,14 @@ int adk_linear(const float* A, int64_t lda, const float* W, const float* bias, i
  *   w_rbf[3F][R], b_rbf[3F], rbf_offset[R] (Gaussian centres in scaled distance), R = num_rbf
  *   x_io[N][F]: in = x, out = (x + dx)/sqrt(2);  vec_out[N][3][F] = vec_in + dvec
  *   (vec_out must not alias vec_in: other rows still read it).
+ *   atom_off[B+1] / n_max: system segmentation; when given (and a system's feature slices fit shared
+ *   memory) each CTA stages one system's xh/vec slices and gathers from shared memory instead of L2.
  */
 int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
                 const float* e_geo, const float* xh, const float* vec_in, const float* w_rbf,
                 const float* b_rbf, const float* rbf_offset, int N, int F, int R, float cutoff,
-                int envelope_exponent, float* x_io, float* vec_out, void* stream);
+                int envelope_exponent, float* x_io, float* vec_out,
+                const int32_t* atom_off, int B, int n_max, void* stream);
 
 /* From vp[N][3][2F] = vec_proj(vec) = (vec1|vec2): dot[N][F] = sum_xyz vec1*vec2 / sqrt(F),
  * cat[N][2F] = [x | sqrt(sum_xyz vec2^2 + 1e-8)].  PaiNNUpdate.forward (painn_denoising.py:602-613). */

@@ -70,23 +70,42 @@ def test_empty_system_raises_value_error(model):
 
 
 @pytest.mark.parametrize("name", ["jit2", "mixed", "tiny", "gas", "skew", "pbc_ttf"])
-def test_forward_matches_oracle_and_reference(name, model, golden, weights):
+@pytest.mark.parametrize("gemm", ["tc", "fp32"])
+def test_forward_matches_oracle_and_reference(name, gemm, model, golden, weights):
+    """Per-layer node features and both outputs, for both GEMM engines (tcgen05 fp16x2-split and
+    exact-fp32 SIMT).  Stated tolerance (all relative to the tensor's max magnitude):
+      * vs the fp64 evaluation of the oracle (ground truth): 1e-5 -- the north-star bar;
+      * vs the fp32 oracle / the unmodified reference's frozen fp32 output: 2e-5, because the
+        reference's own fp32 result sits 3-5e-6 from ground truth on these networks (printed)
+        and the two fp32 evaluations err independently (different summation order)."""
     _reset_sticky_pbc()
     make, pbc = CASES[name]
     b, g = make(), golden(name)
-    tr_o, tr_c = {}, {}
-    o1, o2 = O.painn_forward(weights, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms,
-                             pbc=pbc or (True, True, True), trace=tr_o)
-    f1, f2 = model(_with_pbc(b.clone(), pbc).to("cuda:0"), trace=tr_c)
+    tr32, tr64, tr_c = {}, {}, {}
+    kw = dict(pbc=pbc or (True, True, True))
+    graph = O.generate_graph_values(b.pos.numpy(), b.cell.numpy(), b.natoms, **kw)
+    o32 = O.painn_forward(weights, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms, graph=graph, trace=tr32, **kw)
+    o64 = O.painn_forward(weights, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms, graph=graph, trace=tr64,
+                          dtype=torch.float64, **kw)
+    model.gemm = gemm
+    try:
+        outs = model(_with_pbc(b.clone(), pbc).to("cuda:0"), trace=tr_c)
+    finally:
+        model.gemm = "tc"
+    rel = lambda a, ref: float((a.double().cpu() - ref.double()).abs().max() / ref.double().abs().max())
+    worst = 0.0
     for key in tr_c:
-        ref = tr_o[key]
-        err = float((tr_c[key].cpu() - ref).abs().max() / ref.abs().max())
-        assert err < FEATURE_TOL, (key, err)
-    for got, ref, gk in ((f1, o1, "forces"), (f2, o2, "forces2")):
-        scale = float(ref.abs().max())
-        assert float((got.cpu() - ref).abs().max()) < FEATURE_TOL * scale + 1e-9, gk
-        refg = torch.from_numpy(g[gk])  # the unmodified reference's output
-        assert float((got.cpu() - refg).abs().max()) < FEATURE_TOL * scale + 1e-9, gk
+        e64, e32 = rel(tr_c[key], tr64[key]), rel(tr_c[key], tr32[key])
+        worst = max(worst, e64)
+        assert e64 < FEATURE_TOL, (key, e64)
+        assert e32 < 2 * FEATURE_TOL, (key, e32)
+    for got, r32, r64, gk in zip(outs, o32, o64, ("forces", "forces2")):
+        e64, e32, eref = rel(got, r64), rel(got, r32), rel(r32, r64)
+        egold = rel(got, torch.from_numpy(g[gk]))
+        print(f"{name}/{gemm}/{gk}: cuda-vs-fp64 {e64:.2e}  reference(fp32)-vs-fp64 {eref:.2e}  cuda-vs-reference {egold:.2e}"
+              f"  (worst feature vs fp64 {worst:.2e})")
+        assert e64 < FEATURE_TOL, (gk, e64)
+        assert e32 < 2 * FEATURE_TOL and egold < 2 * FEATURE_TOL, (gk, e32, egold)
 
 
 def test_float_attribute_inputs(model, weights):
