@@ -87,15 +87,21 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
         const int start = P.row_start[t], deg = P.row_deg[t];
         float2 dx = make_float2(0.f, 0.f);
         float2 dv[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        // software pipeline: the CSR records of the next group are fetched while this one is processed
+        int nx_src = 0;
+        float4 nx_geo = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < EG && lane < deg) {
+            nx_src = P.e_src[start + lane];
+            nx_geo = P.e_geo[start + lane];
+        }
         int e0 = 0;
         while (e0 < deg) {
-            // lanes 0..EG-1 fetch one edge record each and derive its scaled distance, envelope, window
-            int my_src = 0, my_klo = 0;
-            float4 my_geo = make_float4(0.f, 0.f, 0.f, 0.f);
+            // lanes 0..EG-1 hold one edge record each; derive scaled distance, envelope, window
+            const int my_src = nx_src;
+            const float4 my_geo = nx_geo;
+            int my_klo = 0;
             float my_s = 0.f, my_env = 0.f;
             if (lane < EG && e0 + lane < deg) {
-                my_src = P.e_src[start + e0 + lane];
-                my_geo = P.e_geo[start + e0 + lane];
                 my_s = my_geo.x * P.inv_cutoff;
                 // polynomial envelope 1 + a s^p + b s^(p+1) + c s^(p+2), zero at and beyond the cutoff
                 float sp = my_s;
@@ -116,6 +122,30 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
                 if (cnt == j && e0 + j < deg && kj >= klo0 && kj - klo0 + NTAPS <= 32) cnt = j + 1;
             }
             const int U = __shfl_sync(ADK_FULL_MASK, my_klo, cnt - 1) - klo0 + NTAPS;
+            if (lane < EG && e0 + cnt + lane < deg) {
+                nx_src = P.e_src[start + e0 + cnt + lane];
+                nx_geo = P.e_geo[start + e0 + cnt + lane];
+            }
+            // issue this group's feature gathers now; they land while the tap loop runs
+            float2 hx[EG][3], vx[EG][3];
+            float rh[EG][3];
+#pragma unroll
+            for (int j = 0; j < EG; ++j) {
+                const int src = __shfl_sync(ADK_FULL_MASK, my_src, j);
+                rh[j][0] = __shfl_sync(ADK_FULL_MASK, my_geo.y, j);
+                rh[j][1] = __shfl_sync(ADK_FULL_MASK, my_geo.z, j);
+                rh[j][2] = __shfl_sync(ADK_FULL_MASK, my_geo.w, j);
+                if (j < cnt) {
+                    const float* xs = P.xh + (size_t)src * 3 * F + f0 + fl;
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) hx[j][g] = *reinterpret_cast<const float2*>(xs + g * F);
+                    if (has_vec) {
+                        const float* vs = P.vec_in + (size_t)src * 3 * F + f0 + fl;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) vx[j][c] = *reinterpret_cast<const float2*>(vs + c * F);
+                    }
+                }
+            }
             // lane m evaluates the Gaussian of tap klo0+m for every edge of the group
             float gv[EG];
             const float mu = s_mu[min(klo0 + lane, R - 1)];
@@ -151,30 +181,21 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
 #pragma unroll
             for (int j = 0; j < EG; ++j) {
                 if (j < cnt) {
-                    const int src = __shfl_sync(ADK_FULL_MASK, my_src, j);
-                    const float rh[3] = {__shfl_sync(ADK_FULL_MASK, my_geo.y, j), __shfl_sync(ADK_FULL_MASK, my_geo.z, j),
-                                         __shfl_sync(ADK_FULL_MASK, my_geo.w, j)};
-                    const float* xs = P.xh + (size_t)src * 3 * F + f0 + fl;
-                    const float2 h1 = *reinterpret_cast<const float2*>(xs);
-                    const float2 h2 = *reinterpret_cast<const float2*>(xs + F);
-                    const float2 h3 = *reinterpret_cast<const float2*>(xs + 2 * F);
-                    dx.x += h1.x * rb[j][0].x;
-                    dx.y += h1.y * rb[j][0].y;
-                    const float m2x = h2.x * rb[j][1].x * inv_sqrt_3, m2y = h2.y * rb[j][1].y * inv_sqrt_3;
-                    const float m3x = h3.x * rb[j][2].x, m3y = h3.y * rb[j][2].y;
+                    dx.x += hx[j][0].x * rb[j][0].x;
+                    dx.y += hx[j][0].y * rb[j][0].y;
+                    const float m2x = hx[j][1].x * rb[j][1].x * inv_sqrt_3, m2y = hx[j][1].y * rb[j][1].y * inv_sqrt_3;
+                    const float m3x = hx[j][2].x * rb[j][2].x, m3y = hx[j][2].y * rb[j][2].y;
                     if (has_vec) {
-                        const float* vs = P.vec_in + (size_t)src * 3 * F + f0 + fl;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const float2 vj = *reinterpret_cast<const float2*>(vs + c * F);
-                            dv[c].x += (vj.x * m2x + m3x * rh[c]) * inv_sqrt_h;
-                            dv[c].y += (vj.y * m2y + m3y * rh[c]) * inv_sqrt_h;
+                            dv[c].x += (vx[j][c].x * m2x + m3x * rh[j][c]) * inv_sqrt_h;
+                            dv[c].y += (vx[j][c].y * m2y + m3y * rh[j][c]) * inv_sqrt_h;
                         }
                     } else {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            dv[c].x += (m3x * rh[c]) * inv_sqrt_h;
-                            dv[c].y += (m3y * rh[c]) * inv_sqrt_h;
+                            dv[c].x += (m3x * rh[j][c]) * inv_sqrt_h;
+                            dv[c].y += (m3y * rh[j][c]) * inv_sqrt_h;
                         }
                     }
                 }
@@ -195,7 +216,6 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
         }
     }
 }
-
 
 // ------------------------------------------------------------------------------------------
 // Staged variant: CTA = (one system) x (slice of SF features).  Every source atom of a system

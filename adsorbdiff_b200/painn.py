@@ -456,11 +456,16 @@ class PaiNN(nn.Module):
             if trace is not None:
                 trace[f"upd{l}.x"], trace[f"upd{l}.vec"] = p.x.clone(), vec.clone()
         vec = p.vec[cur]
-        self._head(p, self.out_forces, p.x, vec, p.out[0], presplit=False)
-        if self.so3_denoising:
-            if self.gemm == "tc":  # the first head's block 1 reused the vec planes: split again
-                self._split(p, vec, F, 3 * N, F, p.sp_v, p.rows_3n, self.V_SCALE)
-            self._head(p, self.out_forces2, p.x, vec, p.out[1], presplit=True)
+        saved_gemm = self.gemm
+        self.gemm = getattr(self, "gemm_heads", None) or saved_gemm
+        try:
+            self._head(p, self.out_forces, p.x, vec, p.out[0], presplit=False)
+            if self.so3_denoising:
+                if self.gemm == "tc":  # the first head's block 1 reused the vec planes: split again
+                    self._split(p, vec, F, 3 * N, F, p.sp_v, p.rows_3n, self.V_SCALE)
+                self._head(p, self.out_forces2, p.x, vec, p.out[1], presplit=True)
+        finally:
+            self.gemm = saved_gemm
 
     def _refuse_training(self) -> None:
         if torch.is_grad_enabled() and self.training:
