@@ -34,13 +34,16 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
+
+using namespace adk::tc;
 
 constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 2, TC_UMMA_K = 16;
 constexpr int TC_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC_PROMOTE = 1;        // k-blocks accumulated in TMEM before promotion to registers
-constexpr int TC_EPI_COLS = 128;     // accumulator columns owned by one epilogue warp
+constexpr int TC_EPI_COLS = TC_BN / 2;  // accumulator columns owned by one epilogue warp
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;                      // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;                      // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;    // 96 KB
@@ -61,77 +64,6 @@ struct TcParams {
     float out_split_scale;
     uint32_t* status;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-// 64-bit shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
-// start>>4 | LBO (unused for swizzled K-major) | SBO = 1024 B between 8-row groups | version 1 | SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void split_store(float v, float scale, __half& hi, __half& lo, bool& overflow) {
-    const float sv = v * scale;
-    overflow |= !(fabsf(sv) <= 65504.0f);
-    hi = __float2half_rn(sv);
-    lo = __float2half_rn(sv - __half2float(hi));
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams P) {
@@ -343,26 +275,39 @@ __global__ void split_f16_kernel(const float* __restrict__ src, int64_t ld, int 
     if (overflow && status) atomicOr(status, ADK_STATUS_F16_OVERFLOW);
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-int g_num_sms = 148;
-
-// 2-D fp16 tensor [rows][K] (K contiguous), box = [box_rows][64], 128-byte swizzle
-int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t K, uint32_t box_rows) {
-    if (!g_encode) return ADK_EINVAL;
-    cuuint64_t dims[2] = {K, rows};
-    cuuint64_t strides[1] = {K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
+// many tensors in one launch: table[i] = {src, dst, n_elems} (dst planes n_elems apart); blockIdx.y = tensor
+struct SplitDesc {
+    const float* src;
+    __half* dst;
+    int64_t n;
+};
+__global__ void split_f16_multi_kernel(const SplitDesc* __restrict__ table, float scale, uint32_t* status) {
+    const SplitDesc d = table[blockIdx.y];
+    bool overflow = false;
+    const int64_t n4 = d.n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(d.src)[i];
+        __align__(8) __half hi[4];
+        __align__(8) __half lo[4];
+        split_store(v.x, scale, hi[0], lo[0], overflow);
+        split_store(v.y, scale, hi[1], lo[1], overflow);
+        split_store(v.z, scale, hi[2], lo[2], overflow);
+        split_store(v.w, scale, hi[3], lo[3], overflow);
+        reinterpret_cast<uint2*>(d.dst)[i] = *reinterpret_cast<const uint2*>(hi);
+        reinterpret_cast<uint2*>(d.dst + d.n)[i] = *reinterpret_cast<const uint2*>(lo);
+    }
+    if (overflow && status) atomicOr(status, ADK_STATUS_F16_OVERFLOW);
 }
 
 }  // namespace
+
+extern "C" int adk_split_f16_multi(const void* table, int count, float scale, uint32_t* status, void* stream) {
+    if (!table || count <= 0) return ADK_EINVAL;
+    split_f16_multi_kernel<<<dim3(64, count), 256, 0, adk::as_stream(stream)>>>(
+        reinterpret_cast<const SplitDesc*>(table), scale, status);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int adk_split_f16(const float* src, int64_t ld, int M, int K, float scale, void* dst, int64_t plane_rows,
                              uint32_t* status, void* stream) {
@@ -384,8 +329,8 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     if (out_split && out_plane_rows < M) return ADK_EINVAL;
     alignas(64) CUtensorMap tmA, tmW;
     int rc;
-    if ((rc = make_map(&tmA, a_split, 2 * (uint64_t)a_plane_rows, (uint64_t)K, TC_BM)) != 0) return rc;
-    if ((rc = make_map(&tmW, w_split, 2 * (uint64_t)N, (uint64_t)K, TC_BN)) != 0) return rc;
+    if ((rc = make_map_f16(&tmA, a_split, 2 * (uint64_t)a_plane_rows, (uint64_t)K, TC_BK, TC_BM)) != 0) return rc;
+    if ((rc = make_map_f16(&tmW, w_split, 2 * (uint64_t)N, (uint64_t)K, TC_BK, TC_BN)) != 0) return rc;
     TcParams P;
     P.M = M; P.N = N; P.K = K;
     P.a_lo_row = (int)a_plane_rows; P.w_lo_row = N;
@@ -396,11 +341,16 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     P.out_split_scale = out_split_scale;
     P.status = status;
     const int tiles = ((M + TC_BM - 1) / TC_BM) * (N / TC_BN);
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    const int grid = tiles < adk::tc::g_num_sms ? tiles : adk::tc::g_num_sms;
     linear_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, adk::as_stream(stream)>>>(tmA, tmW, P);
     ADK_LAUNCH_CHECK();
     return 0;
 }
+
+namespace adk { namespace tc {
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 148;
+} }
 
 int adk_linear_tc_set_attrs() {
     void* fn = nullptr;
@@ -408,9 +358,9 @@ int adk_linear_tc_set_attrs() {
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
     if (e != cudaSuccess) return (int)e;
     if (q != cudaDriverEntryPointSuccess || !fn) return ADK_EINVAL;
-    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    adk::tc::g_encode = reinterpret_cast<adk::tc::EncodeTiledFn>(fn);
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&adk::tc::g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     return (int)cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
 }

@@ -33,6 +33,7 @@ struct NbParams {
     int32_t* row_start;
     int32_t* row_deg;
     int32_t* e_src;
+    int32_t* e_tgt;
     float4* e_geo;
     uint32_t* kept_pack;
     int32_t* kept_cnt;
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(NB_THREADS) neighbors_kernel(NbParams P) {
             for (int q = 0; q < deg; ++q) rank += (keys[q] < key) ? 1 : 0;
             int src = (int)((key >> 16) & 0xffffu), img = (int)(key & 0xffffu);
             P.e_src[start + rank] = a0 + src;
+            P.e_tgt[start + rank] = a0 + t;
             P.e_geo[start + rank] = edge_geometry(s_pos, s_off, C, t, src, img);
         }
         __syncwarp();
@@ -402,9 +404,9 @@ extern "C" int64_t adk_neighbors_smem_bytes(int n_max, int num_images, int max_n
 
 extern "C" int adk_neighbors(const float* pos, const float* cell, const int32_t* atom_off, int B, int n_max,
                              const int32_t rep[3], float cutoff2, int max_nbrs, int32_t* row_start,
-                             int32_t* row_deg, int32_t* e_src, float* e_geo, uint32_t* kept_pack,
+                             int32_t* row_deg, int32_t* e_src, int32_t* e_tgt, float* e_geo, uint32_t* kept_pack,
                              int32_t* kept_cnt, int32_t* sys_counts, uint32_t* status, void* stream) {
-    if (!pos || !cell || !atom_off || !rep || !row_start || !row_deg || !e_src || !e_geo || !kept_pack ||
+    if (!pos || !cell || !atom_off || !rep || !row_start || !row_deg || !e_src || !e_tgt || !e_geo || !kept_pack ||
         !kept_cnt || !sys_counts || !status || B <= 0)
         return ADK_EINVAL;
     const int C = (2 * rep[0] + 1) * (2 * rep[1] + 1) * (2 * rep[2] + 1);
@@ -414,7 +416,7 @@ extern "C" int adk_neighbors(const float* pos, const float* cell, const int32_t*
     P.pos = pos; P.cell = cell; P.atom_off = atom_off;
     P.rep1 = rep[0]; P.rep2 = rep[1]; P.rep3 = rep[2];
     P.cutoff2 = cutoff2; P.k = max_nbrs; P.n_max = n_max;
-    P.row_start = row_start; P.row_deg = row_deg; P.e_src = e_src; P.e_geo = reinterpret_cast<float4*>(e_geo);
+    P.row_start = row_start; P.row_deg = row_deg; P.e_src = e_src; P.e_tgt = e_tgt; P.e_geo = reinterpret_cast<float4*>(e_geo);
     P.kept_pack = kept_pack; P.kept_cnt = kept_cnt; P.sys_counts = sys_counts; P.status = status;
     neighbors_kernel<<<B, NB_THREADS, (size_t)smem, adk::as_stream(stream)>>>(P);
     ADK_LAUNCH_CHECK();

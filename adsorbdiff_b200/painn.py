@@ -209,7 +209,12 @@ class PaiNN(nn.Module):
         self._plan_cache: Optional[_Plan] = None
         # "tc": tcgen05 fp16x2-split GEMMs (fp32 parity, see csrc/linear_tc.cu); "fp32": exact-fp32 SIMT GEMMs
         self.gemm = "tc"
-        self.msg_staged = False  # per-system shared-memory staging variant of the message kernel
+        self.msg_staged = False  # per-system shared-memory staging variant of the SIMT message kernel
+        # message kernel: "mma" = per-system staged, rbf_proj as warp-level mma.sync micro-GEMMs
+        # (csrc/message_mma.cu); "simt" = 16-tap FFMA2 kernel (csrc/message.cu); "tc" = tcgen05 experiment
+        # (csrc/message_tc.cu, parity-green but gather-latency bound)
+        self.msg = "mma"
+        self.msg_comp = 1.1920929e-07  # accumulate-truncation compensation of the message MMA (calibrated)
         self._wsplit_cache: dict = {}
 
     # ------------------------------------------------------------------ reference-facing API
@@ -297,6 +302,7 @@ class PaiNN(nn.Module):
         p.row_start = torch.empty(N, **i32)
         p.row_deg = torch.empty(N, **i32)
         p.e_src = torch.empty(2 * k * N, **i32)
+        p.e_tgt = torch.empty(2 * k * N, **i32)
         p.e_geo = torch.empty(2 * k * N, 4, **f32)
         p.kept_pack = torch.empty(N, k, dtype=torch.int32, device=dev)
         p.kept_cnt = torch.empty(N, **i32)
@@ -326,6 +332,9 @@ class PaiNN(nn.Module):
         p.sp_x = torch.zeros(2 * p.rows_n * 2 * F, **f16)     # node-wise inputs, K <= 2F
         p.sp_h = torch.zeros(2 * p.rows_n * F, **f16)         # hidden of the two-layer MLPs, K <= F
         p.sp_v = torch.zeros(2 * p.rows_3n * F, **f16)        # vec-wise inputs, K <= F
+        p.wt_rbf = [torch.empty(2 * self.num_rbf * 3 * F, **f16) for _ in range(self.num_layers)]
+        # shared-memory footprint of the staged message kernel (see mm_smem_bytes in csrc/message_mma.cu)
+        p.mma_fits = 2 * self.num_rbf * 208 + 4 * self.num_rbf + 4 * p.n_max * 2 * 112 + 64 <= 227 * 1024
         self._plan_cache = p
         return p
 
@@ -333,7 +342,7 @@ class PaiNN(nn.Module):
     def _graph(self, p: _Plan, pos: torch.Tensor) -> None:
         call("adk_neighbors", p.device, ptr(pos), ptr(p.cell_f32), ptr(p.atom_off), p.B, p.n_max, p.rep_c,
              float(self.cutoff * self.cutoff), self.max_neighbors, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src),
-             ptr(p.e_geo), ptr(p.kept_pack), ptr(p.kept_cnt), ptr(p.sys_counts), ptr(p.status))
+             ptr(p.e_tgt), ptr(p.e_geo), ptr(p.kept_pack), ptr(p.kept_cnt), ptr(p.sys_counts), ptr(p.status))
 
     # power-of-two prescales of the fp16x2 split.  hi+lo is exact to 22 bits while |s*x| stays in
     # [2^-3, 65504] (below that the lo plane goes subnormal and the error floor is 2^-25/s absolute):
@@ -348,20 +357,39 @@ class PaiNN(nn.Module):
         call("adk_linear", p.device, ptr(A), lda, ptr(W), ptr(lin.bias) if lin.bias is not None else None,
              M, W.shape[0], W.shape[1], act, ptr(C), ldc)
 
+    def _tc_linears(self):
+        """Every nn.Linear whose weight feeds a tensor-core kernel (N % 256 == 0 GEMMs and rbf_proj)."""
+        out = []
+        for m, u in zip(self.message_layers, self.update_layers):
+            out += [m.x_proj[0], m.x_proj[2], m.rbf_proj, u.vec_proj, u.xvec_proj[0], u.xvec_proj[2]]
+        heads = [self.out_forces] + ([self.out_forces2] if self.so3_denoising else [])
+        for h in heads:
+            b0, b1 = h.output_network
+            out += [b0.vec1_proj, b0.vec2_proj, b0.update_net[0], b0.update_net[2], b1.vec1_proj, b1.update_net[0]]
+        return [l for l in out if l.weight.shape[0] % 128 == 0 and l.weight.shape[1] % 64 == 0]
+
+    def _resplit_weights(self, p) -> None:
+        """fp16x2 planes of all tensor-core weights, rebuilt at the start of EVERY forward in one launch
+        (21 M parameters: ~170 MB of traffic, tens of microseconds).  Parameters may be changed in place at
+        any time -- the reference's EMA does `param.data.copy_()` three times per sampler step, which does
+        not even bump `Parameter._version` -- so no cache keyed on versions can be trusted."""
+        lins = self._tc_linears()
+        key = tuple(l.weight.data_ptr() for l in lins)
+        st = self._wsplit_cache.get("table")
+        if st is None or st[0] != key or st[1].device != p.device:
+            bufs, recs = {}, []
+            for l in lins:
+                n = l.weight.numel()
+                buf = torch.empty(2 * n, dtype=torch.float16, device=p.device)
+                bufs[id(l)] = buf
+                recs += [l.weight.data_ptr(), buf.data_ptr(), n]
+            table = torch.tensor(recs, dtype=torch.int64).to(p.device)
+            st = (key, table, bufs, len(lins))
+            self._wsplit_cache["table"] = st
+        call("adk_split_f16_multi", p.device, ptr(st[1]), st[3], self.W_SCALE, ptr(p.status))
+
     def _wsplit(self, p, lin):
-        """fp16x2 planes of a weight, rebuilt whenever the parameter is modified in place (EMA swaps,
-        load_state_dict, optimizer steps all bump `_version`) or re-allocated."""
-        W = lin.weight
-        key = id(lin)
-        ent = self._wsplit_cache.get(key)
-        if ent is None or ent[0] != W._version or ent[1] != W.data_ptr():
-            n, k = W.shape
-            buf = ent[2] if ent is not None and ent[2].numel() == 2 * n * k and ent[2].device == W.device else \
-                torch.empty(2 * n * k, dtype=torch.float16, device=W.device)
-            call("adk_split_f16", p.device, ptr(W), k, n, k, self.W_SCALE, ptr(buf), n, ptr(p.status))
-            ent = (W._version, W.data_ptr(), buf)
-            self._wsplit_cache[key] = ent
-        return ent[2]
+        return self._wsplit_cache["table"][2][id(lin)]
 
     def _split(self, p, A, lda, M, K, buf, rows, scale=None):
         call("adk_split_f16", p.device, ptr(A), lda, M, K, scale or self.A_SCALE, ptr(buf), rows, ptr(p.status))
@@ -429,6 +457,8 @@ class PaiNN(nn.Module):
         """Enqueue the whole forward on the current stream (capturable: no sync, no allocation)."""
         N, F, R = p.N, self.hidden_channels, self.num_rbf
         dev = p.device
+        if self.gemm == "tc" or self.msg == "tc":
+            self._resplit_weights(p)
         self._graph(p, pos)
         call("adk_embed", dev, ptr(z), ptr(self.atom_emb.embeddings.weight), self.atom_emb.embeddings.weight.shape[0],
              N, F, ptr(p.x), None)
@@ -440,10 +470,25 @@ class PaiNN(nn.Module):
             self._mlp2(p, p.xn, F, N, F, m.x_proj[0], m.x_proj[2], p.xh, 3 * F)
             vin = p.vec[cur] if l > 0 else None  # vec == 0 before the first message
             vout = p.vec[1 - cur]
-            call("adk_message", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(p.xh),
-                 ptr(vin) if vin is not None else None, ptr(m.rbf_proj.weight), ptr(m.rbf_proj.bias),
-                 ptr(self.radial_basis.rbf.offset), N, F, R, float(self.cutoff), self.radial_basis.exponent,
-                 ptr(p.x), ptr(vout), ptr(p.atom_off) if self.msg_staged else None, p.B, p.n_max)
+            if self.msg == "mma" and R <= 128 and R % 16 == 0 and p.mma_fits:
+                wt = p.wt_rbf[l]
+                call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self.W_SCALE, ptr(wt),
+                     ptr(p.status))
+                call("adk_message_mma", dev, ptr(p.atom_off), p.B, p.n_max, ptr(p.row_start), ptr(p.row_deg),
+                     ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wt),
+                     self.W_SCALE, ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R,
+                     float(self.cutoff), self.radial_basis.exponent, float(self.msg_comp), ptr(p.x), ptr(vout))
+            elif self.msg == "tc" and F == 512 and R == 128:
+                wr = self._wsplit(p, m.rbf_proj)
+                call("adk_message_tc", dev, ptr(p.atom_off), p.B, ptr(p.sys_counts), ptr(p.row_deg), ptr(p.e_src),
+                     ptr(p.e_tgt), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wr),
+                     self.W_SCALE, ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R, self.max_neighbors,
+                     float(self.cutoff), self.radial_basis.exponent, float(self.msg_comp), ptr(p.x), ptr(vout))
+            else:
+                call("adk_message", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(p.xh),
+                     ptr(vin) if vin is not None else None, ptr(m.rbf_proj.weight), ptr(m.rbf_proj.bias),
+                     ptr(self.radial_basis.rbf.offset), N, F, R, float(self.cutoff), self.radial_basis.exponent,
+                     ptr(p.x), ptr(vout), ptr(p.atom_off) if self.msg_staged else None, p.B, p.n_max)
             cur = 1 - cur
             vec = p.vec[cur]
             if trace is not None:

@@ -70,7 +70,7 @@ int64_t adk_neighbors_smem_bytes(int n_max, int num_images, int max_nbrs);
  *   cutoff2 = fp32(radius*radius), max_nbrs = k.
  * Outputs (in-edge CSR by target atom; system b owns edge slots [2k*atom_off[b], 2k*atom_off[b+1])):
  *   row_start[N], row_deg[N]  absolute slot of each atom's first in-edge, and its in-degree
- *   e_src[2kN]                global index of the source atom
+ *   e_src[2kN], e_tgt[2kN]    global index of the source / target atom of each in-edge
  *   e_geo[2kN][4]             (d, rx, ry, rz): clamped distance and unit vector target->source image
  *   kept_pack[N][k], kept_cnt[N]  the directed half (j<i rule) in reference order, packed
  *                             (j_local<<16 | image_index), for adk_export_edges
@@ -80,7 +80,7 @@ int64_t adk_neighbors_smem_bytes(int n_max, int num_images, int max_nbrs);
  */
 int adk_neighbors(const float* pos, const float* cell, const int32_t* atom_off, int B, int n_max,
                   const int32_t rep[3] /* host */, float cutoff2, int max_nbrs,
-                  int32_t* row_start, int32_t* row_deg, int32_t* e_src, float* e_geo,
+                  int32_t* row_start, int32_t* row_deg, int32_t* e_src, int32_t* e_tgt, float* e_geo,
                   uint32_t* kept_pack, int32_t* kept_cnt, int32_t* sys_counts,
                   uint32_t* status, void* stream);
 
@@ -129,6 +129,11 @@ int adk_linear(const float* A, int64_t lda, const float* W, const float* bias, i
  */
 int adk_split_f16(const float* src, int64_t ld, int M, int K, float scale, void* dst, int64_t plane_rows,
                   uint32_t* status, void* stream);
+/* Same split for `count` contiguous tensors in one launch: table[i] = {const float* src; fp16* dst;
+ * int64 n_elems} (device array of 24-byte records; dst planes are n_elems apart, n_elems % 4 == 0).
+ * Used to re-split every weight at the start of each forward, so in-place parameter updates
+ * (EMA swaps through `.data`, optimizer steps) can never leave a stale packed copy behind. */
+int adk_split_f16_multi(const void* table, int count, float scale, uint32_t* status, void* stream);
 int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, const void* w_split, int N, int K,
                   const float* bias, float acc_scale, int act, float* out_f32, int64_t ldc,
                   void* out_split, int64_t out_plane_rows, float out_split_scale, uint32_t* status,
@@ -151,6 +156,34 @@ int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t*
                 const float* b_rbf, const float* rbf_offset, int N, int F, int R, float cutoff,
                 int envelope_exponent, float* x_io, float* vec_out,
                 const int32_t* atom_off, int B, int n_max, void* stream);
+
+/*
+ * Tensor-core variant of adk_message: same contract, rbf_proj runs on tcgen05 (fp16x2 split, TMEM
+ * accumulators, weights streamed by TMA), one CTA per system, epilogue threads own one feature and
+ * reduce along the CSR row in registers.  Requires F == 512, R == 128.
+ *   w_rbf_split = adk_split_f16(w_rbf[3F][R], scale = w_scale) -> fp16 [2][3F][R]
+ *   comp = relative compensation of the tensor core's accumulate-truncation bias (see csrc/linear_tc.cu)
+ */
+int adk_message_tc(const int32_t* atom_off, int B, const int32_t* sys_counts, const int32_t* row_deg,
+                   const int32_t* e_src, const int32_t* e_tgt, const float* e_geo, const float* xh,
+                   const float* vec_in, const void* w_rbf_split, float w_scale, const float* b_rbf,
+                   const float* rbf_offset, int F, int R, int max_nbrs, float cutoff,
+                   int envelope_exponent, float comp, float* x_io, float* vec_out, void* stream);
+
+/*
+ * Warp-MMA variant of adk_message (csrc/message_mma.cu): one CTA per (system, 32-feature slice); the
+ * system's xh / vec slices and the fp16x2 planes of the w_rbf slice are staged in shared memory, and
+ * rbfh of 16 distance-sorted edges at a time is a mma.sync m16n8k16 micro-GEMM over the union RBF window.
+ *   wt_split = adk_split_f16_transpose(w_rbf[3F][R], scale = w_scale) -> fp16 [2][R][3F]
+ *   n_max = largest system; returns ADK_ERANGE when a system's slices do not fit shared memory.
+ */
+int adk_split_f16_transpose(const float* w, int rows, int cols, float scale, void* dst, uint32_t* status,
+                            void* stream);
+int adk_message_mma(const int32_t* atom_off, int B, int n_max, const int32_t* row_start,
+                    const int32_t* row_deg, const int32_t* e_src, const float* e_geo, const float* xh,
+                    const float* vec_in, const void* wt_split, float w_scale, const float* b_rbf,
+                    const float* rbf_offset, int F, int R, float cutoff, int envelope_exponent,
+                    float comp, float* x_io, float* vec_out, void* stream);
 
 /* From vp[N][3][2F] = vec_proj(vec) = (vec1|vec2): dot[N][F] = sum_xyz vec1*vec2 / sqrt(F),
  * cat[N][2F] = [x | sqrt(sum_xyz vec2^2 + 1e-8)].  PaiNNUpdate.forward (painn_denoising.py:602-613). */

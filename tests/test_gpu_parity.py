@@ -70,10 +70,10 @@ def test_empty_system_raises_value_error(model):
 
 
 @pytest.mark.parametrize("name", ["jit2", "mixed", "tiny", "gas", "skew", "pbc_ttf"])
-@pytest.mark.parametrize("gemm", ["tc", "fp32"])
-def test_forward_matches_oracle_and_reference(name, gemm, model, golden, weights):
+@pytest.mark.parametrize("gemm,msg", [("tc", "mma"), ("tc", "tc"), ("tc", "simt"), ("fp32", "simt")])
+def test_forward_matches_oracle_and_reference(name, gemm, msg, model, golden, weights):
     """Per-layer node features and both outputs, for both GEMM engines (tcgen05 fp16x2-split and
-    exact-fp32 SIMT).  Stated tolerance (all relative to the tensor's max magnitude):
+    exact-fp32 SIMT) and both message kernels (rbf_proj on tcgen05 / 16-tap SIMT).  Stated tolerance (all relative to the tensor's max magnitude):
       * vs the fp64 evaluation of the oracle (ground truth): 1e-5 -- the north-star bar;
       * vs the fp32 oracle / the unmodified reference's frozen fp32 output: 2e-5, because the
         reference's own fp32 result sits 3-5e-6 from ground truth on these networks (printed)
@@ -87,11 +87,11 @@ def test_forward_matches_oracle_and_reference(name, gemm, model, golden, weights
     o32 = O.painn_forward(weights, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms, graph=graph, trace=tr32, **kw)
     o64 = O.painn_forward(weights, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms, graph=graph, trace=tr64,
                           dtype=torch.float64, **kw)
-    model.gemm = gemm
+    model.gemm, model.msg = gemm, msg
     try:
         outs = model(_with_pbc(b.clone(), pbc).to("cuda:0"), trace=tr_c)
     finally:
-        model.gemm = "tc"
+        model.gemm, model.msg = "tc", "mma"
     rel = lambda a, ref: float((a.double().cpu() - ref.double()).abs().max() / ref.double().abs().max())
     worst = 0.0
     for key in tr_c:
@@ -102,7 +102,7 @@ def test_forward_matches_oracle_and_reference(name, gemm, model, golden, weights
     for got, r32, r64, gk in zip(outs, o32, o64, ("forces", "forces2")):
         e64, e32, eref = rel(got, r64), rel(got, r32), rel(r32, r64)
         egold = rel(got, torch.from_numpy(g[gk]))
-        print(f"{name}/{gemm}/{gk}: cuda-vs-fp64 {e64:.2e}  reference(fp32)-vs-fp64 {eref:.2e}  cuda-vs-reference {egold:.2e}"
+        print(f"{name}/{gemm}+{msg}/{gk}: cuda-vs-fp64 {e64:.2e}  reference(fp32)-vs-fp64 {eref:.2e}  cuda-vs-reference {egold:.2e}"
               f"  (worst feature vs fp64 {worst:.2e})")
         assert e64 < FEATURE_TOL, (gk, e64)
         assert e32 < 2 * FEATURE_TOL and egold < 2 * FEATURE_TOL, (gk, e32, egold)
