@@ -31,9 +31,10 @@ constexpr int MM_WARPS = MM_THREADS / 32;
 constexpr int MM_SF = 32;                       // features per group in a CTA slice
 constexpr int MM_WROW = 208;                    // bytes per centre row of a weight plane: 3 x 64 + 16 pad
 constexpr float MM_RBF_SCALE = 1024.0f;
-// staged source features, per atom: [group 3][column pair qt 4][n-tile 4][2] floats + 16 pad.  A lane's eight
-// features of a group are two float4; the 16-float pad spreads the 8 atoms a warp reads at once over two
-// bank windows (a 96-float stride would put them all on the same banks: measured 49 % conflict wavefronts).
+// staged source features, per atom: [group 3][n-tile pair 2][column pair qt 4][n-tile in pair 2][2] floats + 16 pad.
+// A lane's eight features of a group are two float4, and the four lanes of a quad read 16 CONTIGUOUS words;
+// with a row stride of 112 = 16 (mod 32) words the 8 atoms a warp reads at once alternate between the two
+// halves of the banks (a 96-float stride put them all on the same banks: measured 49 % conflict wavefronts).
 constexpr int MM_SRC_STRIDE = 112;
 
 struct MmParams {
@@ -105,12 +106,12 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     for (int k = threadIdx.x; k < R; k += MM_THREADS) s_mu[k] = P.rbf_offset[k];
     if (threadIdx.x < 96) {
         const int g = threadIdx.x >> 5, f = threadIdx.x & 31;
-        s_bias[g * 32 + ((f >> 1) & 3) * 8 + (f >> 3) * 2 + (f & 1)] = P.b_rbf[g * F + f0 + f];
+        s_bias[g * 32 + (f >> 4) * 16 + ((f >> 1) & 3) * 4 + ((f >> 3) & 1) * 2 + (f & 1)] = P.b_rbf[g * F + f0 + f];
     }
     // ---- stage the system's source features: one 128-byte segment per (atom, group) per warp ----
     {
         // feature f = nt * 8 + 2 * qt + h of the slice lands at [g][qt][nt][h]
-        const int pos = ((lane >> 1) & 3) * 8 + (lane >> 3) * 2 + (lane & 1);
+        const int pos = (lane >> 4) * 16 + ((lane >> 1) & 3) * 4 + ((lane >> 3) & 1) * 2 + (lane & 1);
         for (int seg = warp; seg < n * 3; seg += MM_WARPS) {
             const int j = seg / 3, g = seg - j * 3;
             s_xh[j * MM_SRC_STRIDE + g * 32 + pos] = P.xh[(size_t)(a0 + j) * 3 * F + g * F + f0 + lane];
@@ -226,22 +227,22 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
                 const float ry = __shfl_sync(ADK_FULL_MASK, my_geo.z, er);
                 const float rz = __shfl_sync(ADK_FULL_MASK, my_geo.w, er);
                 if (er < cnt) {
-                    const float* xs = s_xh + (size_t)src * MM_SRC_STRIDE + qt * 8;
-                    const float* vs = s_vec + (size_t)src * MM_SRC_STRIDE + qt * 8;
+                    const float* xs = s_xh + (size_t)src * MM_SRC_STRIDE + qt * 4;
+                    const float* vs = s_vec + (size_t)src * MM_SRC_STRIDE + qt * 4;
                     float h1[8], h2[8], h3[8];
                     *reinterpret_cast<float4*>(h1) = *reinterpret_cast<const float4*>(xs);
-                    *reinterpret_cast<float4*>(h1 + 4) = *reinterpret_cast<const float4*>(xs + 4);
+                    *reinterpret_cast<float4*>(h1 + 4) = *reinterpret_cast<const float4*>(xs + 16);
                     *reinterpret_cast<float4*>(h2) = *reinterpret_cast<const float4*>(xs + 32);
-                    *reinterpret_cast<float4*>(h2 + 4) = *reinterpret_cast<const float4*>(xs + 36);
+                    *reinterpret_cast<float4*>(h2 + 4) = *reinterpret_cast<const float4*>(xs + 48);
                     *reinterpret_cast<float4*>(h3) = *reinterpret_cast<const float4*>(xs + 64);
-                    *reinterpret_cast<float4*>(h3 + 4) = *reinterpret_cast<const float4*>(xs + 68);
+                    *reinterpret_cast<float4*>(h3 + 4) = *reinterpret_cast<const float4*>(xs + 80);
                     float m2[8], b1[8], b2[8], b3[8];
-                    *reinterpret_cast<float4*>(b1) = *reinterpret_cast<const float4*>(s_bias + qt * 8);
-                    *reinterpret_cast<float4*>(b1 + 4) = *reinterpret_cast<const float4*>(s_bias + qt * 8 + 4);
-                    *reinterpret_cast<float4*>(b2) = *reinterpret_cast<const float4*>(s_bias + 32 + qt * 8);
-                    *reinterpret_cast<float4*>(b2 + 4) = *reinterpret_cast<const float4*>(s_bias + 32 + qt * 8 + 4);
-                    *reinterpret_cast<float4*>(b3) = *reinterpret_cast<const float4*>(s_bias + 64 + qt * 8);
-                    *reinterpret_cast<float4*>(b3 + 4) = *reinterpret_cast<const float4*>(s_bias + 64 + qt * 8 + 4);
+                    *reinterpret_cast<float4*>(b1) = *reinterpret_cast<const float4*>(s_bias + qt * 4);
+                    *reinterpret_cast<float4*>(b1 + 4) = *reinterpret_cast<const float4*>(s_bias + qt * 4 + 16);
+                    *reinterpret_cast<float4*>(b2) = *reinterpret_cast<const float4*>(s_bias + 32 + qt * 4);
+                    *reinterpret_cast<float4*>(b2 + 4) = *reinterpret_cast<const float4*>(s_bias + 32 + qt * 4 + 16);
+                    *reinterpret_cast<float4*>(b3) = *reinterpret_cast<const float4*>(s_bias + 64 + qt * 4);
+                    *reinterpret_cast<float4*>(b3 + 4) = *reinterpret_cast<const float4*>(s_bias + 64 + qt * 4 + 16);
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
                         for (int c = 0; c < 3; ++c) {
                             float vj[8];
                             *reinterpret_cast<float4*>(vj) = *reinterpret_cast<const float4*>(vs + c * 32);
-                            *reinterpret_cast<float4*>(vj + 4) = *reinterpret_cast<const float4*>(vs + c * 32 + 4);
+                            *reinterpret_cast<float4*>(vj + 4) = *reinterpret_cast<const float4*>(vs + c * 32 + 16);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) dva[c][i >> 1][i & 1] = fmaf(vj[i], m2[i], dva[c][i >> 1][i & 1]);
                         }
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float2 base = make_float2(0.f, 0.f);
-                    if (has_vec) base = *reinterpret_cast<const float2*>(s_vec + (size_t)tl * MM_SRC_STRIDE + c * 32 + qt * 8 + nt * 2);
+                    if (has_vec) base = *reinterpret_cast<const float2*>(s_vec + (size_t)tl * MM_SRC_STRIDE + c * 32 + (nt >> 1) * 16 + qt * 4 + (nt & 1) * 2);
                     *reinterpret_cast<float2*>(P.vec_out + (size_t)t * 3 * F + c * F + fo) =
                         make_float2(base.x + dva[c][nt][0] * inv_sqrt_h, base.y + dva[c][nt][1] * inv_sqrt_h);
                 }
