@@ -47,7 +47,8 @@ constexpr int TC_EPI_COLS = TC_BN / 2;  // accumulator columns owned by one epil
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;                      // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;                      // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;    // 96 KB
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_MAX_N = 2048;                                          // bias staged in shared memory
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_MAX_N * 4;
 constexpr uint32_t TC_TMEM_COLS = 512;                                  // two 256-column accumulators
 
 struct TcParams {
@@ -65,6 +66,14 @@ struct TcParams {
     uint32_t* status;
 };
 
+// silu(x)/0.6 with fast intrinsics (ex2.approx + approximate reciprocal): ~3e-7 relative, one order below the
+// GEMM's own error; the exact expf + IEEE division version cost ~40 instructions per element and made the
+// epilogue warps, not the tensor pipe, the bottleneck of every ScaledSiLU GEMM.
+__device__ __forceinline__ float ssilu_fast(float x) {
+    return __fdividef(x, 1.0f + __expf(-x)) * (1.0f / 0.6f);
+}
+
+template <int ACT, bool OUT_F32, bool OUT_SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -76,6 +85,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto tfull_bar = [&](int a) { return bar_base + 32u + 8u * a; };
     auto tempty_bar = [&](int a) { return bar_base + 48u + 8u * a; };
     const uint32_t tmem_slot = bar_base + 64u;
+    float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < P.N; i += TC_THREADS) s_bias[i] = P.bias ? P.bias[i] : 0.0f;
 
     const int warp = adk::warp_id(), lane = adk::lane_id();
     const int num_m = (P.M + TC_BM - 1) / TC_BM, num_n = P.N / TC_BN, num_k = P.K / TC_BK;
@@ -212,18 +223,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int n = n0 + c * 32;
                 float o[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float t = acc[c * 32 + j] * P.acc_scale;
-                    if (P.bias) t += __ldg(P.bias + n + j);
-                    o[j] = (P.act == ADK_ACT_SSILU) ? adk::ssilu(t) : t;
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n + 4 * j4);  // broadcast read
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float t = fmaf(acc[c * 32 + 4 * j4 + jj], P.acc_scale, bb[jj]);
+                        o[4 * j4 + jj] = (ACT == ADK_ACT_SSILU) ? ssilu_fast(t) : t;
+                    }
                 }
                 if (row_ok) {
-                    if (P.out_f32) {
+                    if (OUT_F32) {
                         float4* dst = reinterpret_cast<float4*>(P.out_f32 + (int64_t)row * P.ldc + n);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                     }
-                    if (P.out_split) {
+                    if (OUT_SPLIT) {
                         uint32_t ph[16], pl[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -342,7 +357,20 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     P.status = status;
     const int tiles = ((M + TC_BM - 1) / TC_BM) * (N / TC_BN);
     const int grid = tiles < adk::tc::g_num_sms ? tiles : adk::tc::g_num_sms;
-    linear_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, adk::as_stream(stream)>>>(tmA, tmW, P);
+    if (N > TC_MAX_N) return ADK_ERANGE;
+    cudaStream_t st = adk::as_stream(stream);
+#define ADK_TC_LAUNCH(ACT_, F32_, SPL_) linear_tc_kernel<ACT_, F32_, SPL_><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmW, P)
+    const bool f32 = out_f32 != nullptr, spl = out_split != nullptr;
+    if (act == ADK_ACT_SSILU) {
+        if (f32 && spl) ADK_TC_LAUNCH(ADK_ACT_SSILU, true, true);
+        else if (f32) ADK_TC_LAUNCH(ADK_ACT_SSILU, true, false);
+        else ADK_TC_LAUNCH(ADK_ACT_SSILU, false, true);
+    } else {
+        if (f32 && spl) ADK_TC_LAUNCH(ADK_ACT_NONE, true, true);
+        else if (f32) ADK_TC_LAUNCH(ADK_ACT_NONE, true, false);
+        else ADK_TC_LAUNCH(ADK_ACT_NONE, false, true);
+    }
+#undef ADK_TC_LAUNCH
     ADK_LAUNCH_CHECK();
     return 0;
 }
@@ -362,5 +390,13 @@ int adk_linear_tc_set_attrs() {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&adk::tc::g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    return (int)cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaError_t e2 = cudaSuccess;
+#define ADK_TC_ATTR(ACT_, F32_, SPL_)                                                                          \
+    if (e2 == cudaSuccess)                                                                                     \
+        e2 = cudaFuncSetAttribute(linear_tc_kernel<ACT_, F32_, SPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  TC_SMEM_BYTES)
+    ADK_TC_ATTR(ADK_ACT_SSILU, true, true); ADK_TC_ATTR(ADK_ACT_SSILU, true, false); ADK_TC_ATTR(ADK_ACT_SSILU, false, true);
+    ADK_TC_ATTR(ADK_ACT_NONE, true, true); ADK_TC_ATTR(ADK_ACT_NONE, true, false); ADK_TC_ATTR(ADK_ACT_NONE, false, true);
+#undef ADK_TC_ATTR
+    return (int)e2;
 }
