@@ -74,9 +74,9 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
 }
 // two scaled fp32 values -> packed fp16 hi pair and lo pair
 __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-    const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
-    const __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+    const __half2 hh = __floats2half2_rn(v0, v1);       // one cvt.rn.f16x2.f32
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(v0 - back.x, v1 - back.y);
     hi = *reinterpret_cast<const uint32_t*>(&hh);
     lo = *reinterpret_cast<const uint32_t*>(&ll);
 }
