@@ -33,7 +33,7 @@ SIGNATURES = {
     "adk_export_edges": (c_int, [_P, _P, _P, c_int, ctypes.POINTER(c_int32), c_int, _P, _P, _P, _P,
                                  _P, c_int64, _P, _P, _P, _P, _P]),
     "adk_embed": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
-    "adk_layernorm": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P]),
+    "adk_layernorm": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P, c_int64, c_float, _P, _P]),
     "adk_linear": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int, c_int, _P, c_int64, _P]),
     "adk_split_f16": (c_int, [_P, c_int64, c_int, c_int, c_float, _P, c_int64, _P, _P]),
     "adk_split_f16_multi": (c_int, [_P, c_int, c_float, _P, _P]),
@@ -45,10 +45,10 @@ SIGNATURES = {
                                c_float, c_int, c_float, _P, _P, _P]),
     "adk_split_f16_transpose": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P]),
     "adk_message_mma": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_int, c_int,
-                                c_float, c_int, c_float, _P, _P, _P]),
-    "adk_update_prep": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
+                                c_float, c_int, c_float, _P, _P, _P, c_int64, c_float, _P, _P]),
+    "adk_update_prep": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int64, c_float, _P, _P]),
     "adk_update_gate": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
-    "adk_head_prep": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "adk_head_prep": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int64, c_float, _P, _P]),
     "adk_head_gate": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "adk_init_placement": (c_int, [_P, _P, _P, _P, _P, c_int, _P]),
     "adk_se3_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),

@@ -1,5 +1,6 @@
 // Shared helpers for the adsorbdiff_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -42,6 +43,14 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
     unsigned long long rd;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2*>(&rd);
+}
+
+// fp16x2 split of one value for the tensor-core GEMM operands: hi = fp16(s*v), lo = fp16(s*v - hi)
+__device__ __forceinline__ void split_f16x2(float v, float scale, __half& hi, __half& lo, bool& overflow) {
+    const float sv = v * scale;
+    overflow |= !(fabsf(sv) <= 65504.0f);
+    hi = __float2half_rn(sv);
+    lo = __float2half_rn(sv - __half2float(hi));
 }
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -54,6 +54,10 @@ struct MmParams {
     float acc_scale;
     float* x_io;
     float* vec_out;
+    __half* vsplit;        // optional fp16x2 planes of vec_out, [2][vsplit_rows][F] (row = atom * 3 + xyz)
+    int64_t vsplit_plane;
+    float vsplit_scale;
+    uint32_t* status;
 };
 
 __host__ __device__ inline size_t mm_smem_bytes(int R, int n_max) {
@@ -270,33 +274,75 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
                 }
             }
         }
-        // segmented sum: reduce over the 8 lanes that share this column pair, lanes 0..3 write
+        // segmented sum over the row's edges = sum over the 8 lanes that share this column pair (qt).  Done as a
+        // reduce-scatter: 32 partial values per lane (16 float2 outputs: dx[4 n-tiles], dvec[3][4]) are halved three
+        // times (xor 16, 8, 4), 28 shuffles instead of 96, and every lane ends up owning TWO finished outputs,
+        // so the write-out (fp32 + fp16x2 planes) is spread over all 32 lanes instead of 4.
+        float v32[32];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 4; ++nt) {
+            v32[2 * nt] = dxa[nt][0];
+            v32[2 * nt + 1] = dxa[nt][1];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    dxa[nt][h] += __shfl_xor_sync(ADK_FULL_MASK, dxa[nt][h], o);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) dva[c][nt][h] += __shfl_xor_sync(ADK_FULL_MASK, dva[c][nt][h], o);
-                }
+            for (int c = 0; c < 3; ++c) {
+                v32[8 + (c * 4 + nt) * 2] = dva[c][nt][0];
+                v32[8 + (c * 4 + nt) * 2 + 1] = dva[c][nt][1];
             }
-        if (lane < 4) {
+        }
+        float v16[16], v8[8], v4[4];
+        {
+            const bool up = (lane & 16) != 0;
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const int fo = f0 + nt * 8 + 2 * qt;
+            for (int i = 0; i < 16; ++i) {
+                const float mine = up ? v32[16 + i] : v32[i], other = up ? v32[i] : v32[16 + i];
+                v16[i] = mine + __shfl_xor_sync(ADK_FULL_MASK, other, 16);
+            }
+        }
+        {
+            const bool up = (lane & 8) != 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float mine = up ? v16[8 + i] : v16[i], other = up ? v16[i] : v16[8 + i];
+                v8[i] = mine + __shfl_xor_sync(ADK_FULL_MASK, other, 8);
+            }
+        }
+        {
+            const bool up = (lane & 4) != 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float mine = up ? v8[4 + i] : v8[i], other = up ? v8[i] : v8[4 + i];
+                v4[i] = mine + __shfl_xor_sync(ADK_FULL_MASK, other, 4);
+            }
+        }
+        // this lane owns outputs o0 = 2 * blk and o0 + 1 (o < 4: dx of n-tile o; else dvec[(o-4)/4] of n-tile (o-4)%4)
+        const int blk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int o = 2 * blk + w;
+            const float rx0 = v4[2 * w], rx1 = v4[2 * w + 1];
+            if (o < 4) {
+                const int fo = f0 + o * 8 + 2 * qt;
                 float2* xo = reinterpret_cast<float2*>(P.x_io + (size_t)t * F + fo);
                 float2 xv = *xo;
-                xv.x = (xv.x + dxa[nt][0]) * 0.70710678118654752440f;
-                xv.y = (xv.y + dxa[nt][1]) * 0.70710678118654752440f;
+                xv.x = (xv.x + rx0) * 0.70710678118654752440f;
+                xv.y = (xv.y + rx1) * 0.70710678118654752440f;
                 *xo = xv;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float2 base = make_float2(0.f, 0.f);
-                    if (has_vec) base = *reinterpret_cast<const float2*>(s_vec + (size_t)tl * MM_SRC_STRIDE + c * 32 + (nt >> 1) * 16 + qt * 4 + (nt & 1) * 2);
-                    *reinterpret_cast<float2*>(P.vec_out + (size_t)t * 3 * F + c * F + fo) =
-                        make_float2(base.x + dva[c][nt][0] * inv_sqrt_h, base.y + dva[c][nt][1] * inv_sqrt_h);
+            } else {
+                const int c = (o - 4) >> 2, nt = (o - 4) & 3;
+                const int fo = f0 + nt * 8 + 2 * qt;
+                float2 base = make_float2(0.f, 0.f);
+                if (has_vec) base = *reinterpret_cast<const float2*>(s_vec + (size_t)tl * MM_SRC_STRIDE + c * 32 + (nt >> 1) * 16 + qt * 4 + (nt & 1) * 2);
+                const float2 vo = make_float2(base.x + rx0 * inv_sqrt_h, base.y + rx1 * inv_sqrt_h);
+                *reinterpret_cast<float2*>(P.vec_out + (size_t)t * 3 * F + c * F + fo) = vo;
+                if (P.vsplit) {  // operand planes of the vec_proj GEMM that follows
+                    __half h0, l0, h1, l1;
+                    bool overflow = false;
+                    adk::split_f16x2(vo.x, P.vsplit_scale, h0, l0, overflow);
+                    adk::split_f16x2(vo.y, P.vsplit_scale, h1, l1, overflow);
+                    const size_t off = ((size_t)t * 3 + c) * F + fo;
+                    *reinterpret_cast<__half2*>(P.vsplit + off) = __halves2half2(h0, h1);
+                    *reinterpret_cast<__half2*>(P.vsplit + P.vsplit_plane + off) = __halves2half2(l0, l1);
+                    if (overflow && P.status) atomicOr(P.status, ADK_STATUS_F16_OVERFLOW);
                 }
             }
         }
@@ -340,7 +386,8 @@ extern "C" int adk_message_mma(const int32_t* atom_off, int B, int n_max, const 
                                const int32_t* row_deg, const int32_t* e_src, const float* e_geo, const float* xh,
                                const float* vec_in, const void* wt_split, float w_scale, const float* b_rbf,
                                const float* rbf_offset, int F, int R, float cutoff, int envelope_exponent,
-                               float comp, float* x_io, float* vec_out, void* stream) {
+                               float comp, float* x_io, float* vec_out, void* vec_split, int64_t split_rows,
+                               float split_scale, uint32_t* status, void* stream) {
     if (!atom_off || !row_start || !row_deg || !e_src || !e_geo || !xh || !wt_split || !b_rbf || !rbf_offset ||
         !x_io || !vec_out || B <= 0 || n_max <= 0)
         return ADK_EINVAL;
@@ -364,6 +411,8 @@ extern "C" int adk_message_mma(const int32_t* atom_off, int B, int n_max, const 
     P.env_c = (float)(-p * (p + 1) / 2);
     P.acc_scale = (1.0f + comp) / (MM_RBF_SCALE * w_scale);
     P.x_io = x_io; P.vec_out = vec_out;
+    P.vsplit = reinterpret_cast<__half*>(vec_split); P.vsplit_plane = split_rows * (int64_t)F;
+    P.vsplit_scale = split_scale; P.status = status;
     message_mma_kernel<<<dim3(B, F / MM_SF), MM_THREADS, smem, adk::as_stream(stream)>>>(P);
     ADK_LAUNCH_CHECK();
     return 0;

@@ -26,7 +26,8 @@ __global__ void embed_kernel(const int64_t* __restrict__ z, const float* __restr
 
 // one warp per row; two-pass (mean, then biased variance) like torch's CPU LayerNorm
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, int M, int F, float eps, float* __restrict__ y) {
+                                 const float* __restrict__ beta, int M, int F, float eps, float* __restrict__ y,
+                                 __half* __restrict__ sp, int64_t plane, float sp_scale, uint32_t* status) {
     const int row = blockIdx.x * (blockDim.x >> 5) + adk::warp_id();
     if (row >= M) return;
     const int lane = adk::lane_id();
@@ -37,12 +38,23 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     float v = 0.f;
     for (int f = lane; f < F; f += 32) { float d = xr[f] - mean; v += d * d; }
     const float rstd = rsqrtf(adk::warp_sum(v) / (float)F + eps);
-    float* yr = y + (int64_t)row * F;
-    for (int f = lane; f < F; f += 32) yr[f] = (xr[f] - mean) * rstd * gamma[f] + beta[f];
+    bool overflow = false;
+    for (int f = lane; f < F; f += 32) {
+        const float v = (xr[f] - mean) * rstd * gamma[f] + beta[f];
+        if (y) y[(int64_t)row * F + f] = v;
+        if (sp) {  // fp16x2 planes for the tensor-core GEMM that consumes the normalised features
+            __half hi, lo;
+            adk::split_f16x2(v, sp_scale, hi, lo, overflow);
+            sp[(int64_t)row * F + f] = hi;
+            sp[plane + (int64_t)row * F + f] = lo;
+        }
+    }
+    if (overflow && status) atomicOr(status, ADK_STATUS_F16_OVERFLOW);
 }
 
 __global__ void update_prep_kernel(const float* __restrict__ x, const float* __restrict__ vp, int N, int F,
-                                   float inv_sqrt_h, float* __restrict__ dot, float* __restrict__ cat) {
+                                   float inv_sqrt_h, float* __restrict__ dot, float* __restrict__ cat,
+                                   __half* __restrict__ sp, int64_t plane, float sp_scale, uint32_t* status) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)N * F) return;
     const int nidx = (int)(idx / F), f = (int)(idx - (int64_t)nidx * F);
@@ -55,8 +67,22 @@ __global__ void update_prep_kernel(const float* __restrict__ x, const float* __r
         q += v2 * v2;
     }
     dot[idx] = d * inv_sqrt_h;
-    cat[(int64_t)nidx * 2 * F + f] = x[idx];
-    cat[(int64_t)nidx * 2 * F + F + f] = sqrtf(q + 1e-8f);
+    const float c0 = x[idx], c1 = sqrtf(q + 1e-8f);
+    if (cat) {
+        cat[(int64_t)nidx * 2 * F + f] = c0;
+        cat[(int64_t)nidx * 2 * F + F + f] = c1;
+    }
+    if (sp) {
+        bool overflow = false;
+        __half hi, lo;
+        adk::split_f16x2(c0, sp_scale, hi, lo, overflow);
+        sp[(int64_t)nidx * 2 * F + f] = hi;
+        sp[plane + (int64_t)nidx * 2 * F + f] = lo;
+        adk::split_f16x2(c1, sp_scale, hi, lo, overflow);
+        sp[(int64_t)nidx * 2 * F + F + f] = hi;
+        sp[plane + (int64_t)nidx * 2 * F + F + f] = lo;
+        if (overflow && status) atomicOr(status, ADK_STATUS_F16_OVERFLOW);
+    }
 }
 
 __global__ void update_gate_kernel(const float* __restrict__ h, const float* __restrict__ dot,
@@ -79,14 +105,29 @@ __global__ void update_gate_kernel(const float* __restrict__ h, const float* __r
 }
 
 __global__ void head_prep_kernel(const float* __restrict__ x, const float* __restrict__ v1p, int N, int C,
-                                 float* __restrict__ cat) {
+                                 float* __restrict__ cat, __half* __restrict__ sp, int64_t plane, float sp_scale,
+                                 uint32_t* status) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)N * C) return;
     const int nidx = (int)(idx / C), f = (int)(idx - (int64_t)nidx * C);
     const float* r = v1p + (int64_t)nidx * 3 * C;
     float q = r[f] * r[f] + r[C + f] * r[C + f] + r[2 * C + f] * r[2 * C + f];
-    cat[(int64_t)nidx * 2 * C + f] = x[idx];
-    cat[(int64_t)nidx * 2 * C + C + f] = sqrtf(q);  // torch.norm(dim=-2), no epsilon
+    const float c0 = x[idx], c1 = sqrtf(q);  // torch.norm(dim=-2), no epsilon
+    if (cat) {
+        cat[(int64_t)nidx * 2 * C + f] = c0;
+        cat[(int64_t)nidx * 2 * C + C + f] = c1;
+    }
+    if (sp) {
+        bool overflow = false;
+        __half hi, lo;
+        adk::split_f16x2(c0, sp_scale, hi, lo, overflow);
+        sp[(int64_t)nidx * 2 * C + f] = hi;
+        sp[plane + (int64_t)nidx * 2 * C + f] = lo;
+        adk::split_f16x2(c1, sp_scale, hi, lo, overflow);
+        sp[(int64_t)nidx * 2 * C + C + f] = hi;
+        sp[plane + (int64_t)nidx * 2 * C + C + f] = lo;
+        if (overflow && status) atomicOr(status, ADK_STATUS_F16_OVERFLOW);
+    }
 }
 
 __global__ void head_gate_kernel(const float* __restrict__ u, const float* __restrict__ v2p, int N, int Co,
@@ -116,18 +157,22 @@ extern "C" int adk_embed(const int64_t* z, const float* emb, int num_elements, i
 }
 
 extern "C" int adk_layernorm(const float* x, const float* gamma, const float* beta, int M, int F, float eps,
-                             float* y, void* stream) {
-    if (!x || !gamma || !beta || !y || M <= 0 || F <= 0) return ADK_EINVAL;
-    layernorm_kernel<<<blocks_for(M, 8), 256, 0, adk::as_stream(stream)>>>(x, gamma, beta, M, F, eps, y);
+                             float* y, void* y_split, int64_t split_rows, float split_scale, uint32_t* status,
+                             void* stream) {
+    if (!x || !gamma || !beta || (!y && !y_split) || M <= 0 || F <= 0 || (y_split && split_rows < M)) return ADK_EINVAL;
+    layernorm_kernel<<<blocks_for(M, 8), 256, 0, adk::as_stream(stream)>>>(
+        x, gamma, beta, M, F, eps, y, reinterpret_cast<__half*>(y_split), split_rows * (int64_t)F, split_scale, status);
     ADK_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int adk_update_prep(const float* x, const float* vp, int N, int F, float* dot, float* cat,
+                               void* cat_split, int64_t split_rows, float split_scale, uint32_t* status,
                                void* stream) {
-    if (!x || !vp || !dot || !cat || N <= 0 || F <= 0) return ADK_EINVAL;
+    if (!x || !vp || !dot || (!cat && !cat_split) || N <= 0 || F <= 0 || (cat_split && split_rows < N)) return ADK_EINVAL;
     update_prep_kernel<<<blocks_for((int64_t)N * F, 256), 256, 0, adk::as_stream(stream)>>>(
-        x, vp, N, F, 1.0f / sqrtf((float)F), dot, cat);
+        x, vp, N, F, 1.0f / sqrtf((float)F), dot, cat, reinterpret_cast<__half*>(cat_split),
+        split_rows * 2 * (int64_t)F, split_scale, status);
     ADK_LAUNCH_CHECK();
     return 0;
 }
@@ -141,9 +186,11 @@ extern "C" int adk_update_gate(const float* h, const float* dot, const float* vp
     return 0;
 }
 
-extern "C" int adk_head_prep(const float* x, const float* v1p, int N, int C, float* cat, void* stream) {
-    if (!x || !v1p || !cat || N <= 0 || C <= 0) return ADK_EINVAL;
-    head_prep_kernel<<<blocks_for((int64_t)N * C, 256), 256, 0, adk::as_stream(stream)>>>(x, v1p, N, C, cat);
+extern "C" int adk_head_prep(const float* x, const float* v1p, int N, int C, float* cat, void* cat_split,
+                             int64_t split_rows, float split_scale, uint32_t* status, void* stream) {
+    if (!x || !v1p || (!cat && !cat_split) || N <= 0 || C <= 0 || (cat_split && split_rows < N)) return ADK_EINVAL;
+    head_prep_kernel<<<blocks_for((int64_t)N * C, 256), 256, 0, adk::as_stream(stream)>>>(
+        x, v1p, N, C, cat, reinterpret_cast<__half*>(cat_split), split_rows * 2 * (int64_t)C, split_scale, status);
     ADK_LAUNCH_CHECK();
     return 0;
 }

@@ -404,16 +404,19 @@ class PaiNN(nn.Module):
              ptr(out_f32) if out_f32 is not None else None, ldc,
              ptr(out_split) if out_split is not None else None, out_rows, self.A_SCALE, ptr(p.status))
 
-    def _mlp2(self, p, A, lda, M, K, lin0, lin1, out, ldc):
-        """out = lin1(ssilu(lin0(A))): the two-layer MLP shape shared by x_proj, xvec_proj and update_net."""
+    def _mlp2(self, p, A, lda, M, K, lin0, lin1, out, ldc, presplit=False):
+        """out = lin1(ssilu(lin0(A))): the two-layer MLP shape shared by x_proj, xvec_proj and update_net.
+        `presplit`: the producer kernel already wrote the fp16x2 planes of A into p.sp_x."""
         if self.gemm == "tc" and lin1.weight.shape[0] % 256 == 0:
             rows = p.rows_n
-            self._split(p, A, lda, M, K, p.sp_x, rows)
+            if not presplit:
+                self._split(p, A, lda, M, K, p.sp_x, rows)
             self._linear_tc(p, p.sp_x, rows, M, lin0, _cabi.ACT_SSILU, out_split=p.sp_h, out_rows=rows)
             self._linear_tc(p, p.sp_h, rows, M, lin1, _cabi.ACT_NONE, out_f32=out, ldc=ldc)
         elif self.gemm == "tc":
             rows = p.rows_n
-            self._split(p, A, lda, M, K, p.sp_x, rows)
+            if not presplit:
+                self._split(p, A, lda, M, K, p.sp_x, rows)
             self._linear_tc(p, p.sp_x, rows, M, lin0, _cabi.ACT_SSILU, out_f32=p.h1, ldc=lin0.weight.shape[0])
             self._linear(p, p.h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
         else:
@@ -444,13 +447,16 @@ class PaiNN(nn.Module):
         dev = p.device
         # block 0: F -> H
         self._vec_linear(p, vec, F, [(b0.vec1_proj, p.v1p), (b0.vec2_proj, p.v2p)], presplit=presplit)
-        call("adk_head_prep", dev, ptr(x), ptr(p.v1p), N, F, ptr(p.cat))
-        self._mlp2(p, p.cat, 2 * F, N, 2 * F, b0.update_net[0], b0.update_net[2], p.xn, F)  # (s|g), 2*H = F wide
+        tc = self.gemm == "tc"
+        call("adk_head_prep", dev, ptr(x), ptr(p.v1p), N, F, None if tc else ptr(p.cat), ptr(p.sp_x) if tc else None,
+             p.rows_n, self.A_SCALE, ptr(p.status))
+        self._mlp2(p, p.cat, 2 * F, N, 2 * F, b0.update_net[0], b0.update_net[2], p.xn, F, presplit=tc)  # (s|g)
         call("adk_head_gate", dev, ptr(p.xn), ptr(p.v2p), N, H, ptr(p.hx), ptr(p.hv))
         # block 1: H -> 1
         self._vec_linear(p, p.hv, H, [(b1.vec1_proj, p.v1p), (b1.vec2_proj, p.v2p2)])
-        call("adk_head_prep", dev, ptr(p.hx), ptr(p.v1p), N, H, ptr(p.cat))
-        self._mlp2(p, p.cat, 2 * H, N, 2 * H, b1.update_net[0], b1.update_net[2], p.ho2, 2)
+        call("adk_head_prep", dev, ptr(p.hx), ptr(p.v1p), N, H, None if tc else ptr(p.cat), ptr(p.sp_x) if tc else None,
+             p.rows_n, self.A_SCALE, ptr(p.status))
+        self._mlp2(p, p.cat, 2 * H, N, 2 * H, b1.update_net[0], b1.update_net[2], p.ho2, 2, presplit=tc)
         call("adk_head_gate", dev, ptr(p.ho2), ptr(p.v2p2), N, 1, None, ptr(out))
 
     def _run(self, p: _Plan, z: torch.Tensor, pos: torch.Tensor, trace: Optional[dict] = None):
@@ -465,11 +471,14 @@ class PaiNN(nn.Module):
         cur = 0
         for l in range(self.num_layers):
             m, u = self.message_layers[l], self.update_layers[l]
+            tc = self.gemm == "tc"
             call("adk_layernorm", dev, ptr(p.x), ptr(m.x_layernorm.weight), ptr(m.x_layernorm.bias), N, F,
-                 float(m.x_layernorm.eps), ptr(p.xn))
-            self._mlp2(p, p.xn, F, N, F, m.x_proj[0], m.x_proj[2], p.xh, 3 * F)
+                 float(m.x_layernorm.eps), None if tc else ptr(p.xn), ptr(p.sp_x) if tc else None, p.rows_n,
+                 self.A_SCALE, ptr(p.status))
+            self._mlp2(p, p.xn, F, N, F, m.x_proj[0], m.x_proj[2], p.xh, 3 * F, presplit=tc)
             vin = p.vec[cur] if l > 0 else None  # vec == 0 before the first message
             vout = p.vec[1 - cur]
+            vec_presplit = False
             if self.msg == "mma" and R <= 128 and R % 16 == 0 and p.mma_fits:
                 wt = p.wt_rbf[l]
                 call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self.W_SCALE, ptr(wt),
@@ -477,7 +486,9 @@ class PaiNN(nn.Module):
                 call("adk_message_mma", dev, ptr(p.atom_off), p.B, p.n_max, ptr(p.row_start), ptr(p.row_deg),
                      ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wt),
                      self.W_SCALE, ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R,
-                     float(self.cutoff), self.radial_basis.exponent, float(self.msg_comp), ptr(p.x), ptr(vout))
+                     float(self.cutoff), self.radial_basis.exponent, float(self.msg_comp), ptr(p.x), ptr(vout),
+                     ptr(p.sp_v) if tc else None, p.rows_3n, self.V_SCALE, ptr(p.status))
+                vec_presplit = tc
             elif self.msg == "tc" and F == 512 and R == 128:
                 wr = self._wsplit(p, m.rbf_proj)
                 call("adk_message_tc", dev, ptr(p.atom_off), p.B, ptr(p.sys_counts), ptr(p.row_deg), ptr(p.e_src),
@@ -493,9 +504,10 @@ class PaiNN(nn.Module):
             vec = p.vec[cur]
             if trace is not None:
                 trace[f"msg{l}.x"], trace[f"msg{l}.vec"] = p.x.clone(), vec.clone()
-            self._vec_linear(p, vec, F, [(u.vec_proj, p.vp)])
-            call("adk_update_prep", dev, ptr(p.x), ptr(p.vp), N, F, ptr(p.dot), ptr(p.cat))
-            self._mlp2(p, p.cat, 2 * F, N, 2 * F, u.xvec_proj[0], u.xvec_proj[2], p.xh, 3 * F)
+            self._vec_linear(p, vec, F, [(u.vec_proj, p.vp)], presplit=vec_presplit)
+            call("adk_update_prep", dev, ptr(p.x), ptr(p.vp), N, F, ptr(p.dot), None if tc else ptr(p.cat),
+                 ptr(p.sp_x) if tc else None, p.rows_n, self.A_SCALE, ptr(p.status))
+            self._mlp2(p, p.cat, 2 * F, N, 2 * F, u.xvec_proj[0], u.xvec_proj[2], p.xh, 3 * F, presplit=tc)
             sc = getattr(self, "upd_out_scalar_scale_%d" % l).scale_factor
             call("adk_update_gate", dev, ptr(p.xh), ptr(p.dot), ptr(p.vp), ptr(sc), N, F, ptr(p.x), ptr(vec))
             if trace is not None:

@@ -106,7 +106,8 @@ int adk_embed(const int64_t* z, const float* emb, int num_elements, int N, int F
 /* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5).  Replaces
  * PaiNNMessage.x_layernorm (painn_denoising.py:517,531). */
 int adk_layernorm(const float* x, const float* gamma, const float* beta, int M, int F, float eps,
-                  float* y, void* stream);
+                  float* y /* may be NULL */, void* y_split /* fp16 [2][split_rows][F] or NULL */,
+                  int64_t split_rows, float split_scale, uint32_t* status, void* stream);
 
 /* C[M][N] = act(A[M][K] . W[N][K]^T + bias[N]); lda/ldc in elements; bias may be NULL.
  * The dense contractions of PaiNNMessage.x_proj (painn_denoising.py:508-512,531),
@@ -183,11 +184,15 @@ int adk_message_mma(const int32_t* atom_off, int B, int n_max, const int32_t* ro
                     const int32_t* row_deg, const int32_t* e_src, const float* e_geo, const float* xh,
                     const float* vec_in, const void* wt_split, float w_scale, const float* b_rbf,
                     const float* rbf_offset, int F, int R, float cutoff, int envelope_exponent,
-                    float comp, float* x_io, float* vec_out, void* stream);
+                    float comp, float* x_io, float* vec_out,
+                    void* vec_split /* fp16 [2][split_rows][F], row = atom*3+xyz, or NULL */, int64_t split_rows,
+                    float split_scale, uint32_t* status, void* stream);
 
 /* From vp[N][3][2F] = vec_proj(vec) = (vec1|vec2): dot[N][F] = sum_xyz vec1*vec2 / sqrt(F),
  * cat[N][2F] = [x | sqrt(sum_xyz vec2^2 + 1e-8)].  PaiNNUpdate.forward (painn_denoising.py:602-613). */
-int adk_update_prep(const float* x, const float* vp, int N, int F, float* dot, float* cat, void* stream);
+int adk_update_prep(const float* x, const float* vp, int N, int F, float* dot, float* cat /* may be NULL */,
+                    void* cat_split /* fp16 [2][split_rows][2F] or NULL */, int64_t split_rows, float split_scale,
+                    uint32_t* status, void* stream);
 
 /* h[N][3F] = (a|b|c): x = (x + (a + b*dot)/sqrt(2)) * scale ; vec += c * vec1 (vec1 = vp[:, :, :F]).
  * PaiNNUpdate.forward (:614-623), PaiNN.forward (:449-451), ScaleFactor.forward
@@ -198,7 +203,9 @@ int adk_update_gate(const float* h, const float* dot, const float* vp, const flo
 /* GatedEquivariantBlock (painn_denoising.py:688-697), the parts around its linears:
  * prep: cat[N][2C] = [x | ||v1p||_xyz] from v1p[N][3][C] = vec1_proj(v);
  * gate: from u[N][2*Co] = (s|g): x_out[N][Co] = ssilu(s), v_out[N][3][Co] = g * v2p (v2p = vec2_proj(v)). */
-int adk_head_prep(const float* x, const float* v1p, int N, int C, float* cat, void* stream);
+int adk_head_prep(const float* x, const float* v1p, int N, int C, float* cat /* may be NULL */,
+                  void* cat_split /* fp16 [2][split_rows][2C] or NULL */, int64_t split_rows, float split_scale,
+                  uint32_t* status, void* stream);
 int adk_head_gate(const float* u, const float* v2p, int N, int Co, float* x_out, float* v_out, void* stream);
 
 /*
