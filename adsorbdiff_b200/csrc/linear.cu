@@ -105,6 +105,35 @@ __global__ void __launch_bounds__(LT, 2) linear_kernel(const float* __restrict__
     }
 }
 
+// N <= 4 outputs (the 1- and 2-column linears that end the output heads): one warp per row, a 128x128 tile
+// would waste 98 % of its work.  Summation: per-lane partials in K order, then a shuffle tree.
+__global__ void linear_small_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W,
+                                    const float* __restrict__ bias, int M, int N, int K, int act,
+                                    float* __restrict__ C, int64_t ldc) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + adk::warp_id();
+    if (row >= M) return;
+    const int lane = adk::lane_id();
+    const float* a = A + (int64_t)row * lda;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane * 4; k < K; k += 128) {
+        const float4 av = *reinterpret_cast<const float4*>(a + k);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            if (n < N) {
+                const float4 wv = *reinterpret_cast<const float4*>(W + (int64_t)n * K + k);
+                acc[n] = fmaf(av.x, wv.x, fmaf(av.y, wv.y, fmaf(av.z, wv.z, fmaf(av.w, wv.w, acc[n]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        if (n < N) {
+            const float v = adk::warp_sum(acc[n]) + (bias ? bias[n] : 0.f);
+            if (lane == 0) C[(int64_t)row * ldc + n] = apply_act(v, act);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int adk_linear(const float* A, int64_t lda, const float* W, const float* bias, int M, int N, int K,
@@ -112,6 +141,11 @@ extern "C" int adk_linear(const float* A, int64_t lda, const float* W, const flo
     if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || (K % BK) != 0 || (lda & 3) != 0 ||
         (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
         return ADK_EINVAL;
+    if (N <= 4 && (K & 3) == 0) {
+        linear_small_kernel<<<(M + 7) / 8, 256, 0, adk::as_stream(stream)>>>(A, lda, W, bias, M, N, K, act, C, ldc);
+        ADK_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
     linear_kernel<<<grid, LT, 0, adk::as_stream(stream)>>>(A, lda, W, bias, M, N, K, act, C, ldc);
     ADK_LAUNCH_CHECK();

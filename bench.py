@@ -287,19 +287,25 @@ def run_ours(args):
     value = world * S_per * args.steps / (ms / 1e3)
     model.check_status(plan)
 
-    # ---- e2e: same steps through host buffers (pinned H2D of inputs, D2H of result, every step) ----
+    # ---- e2e: the same steps through the public API with HOST buffers ------------------------------
+    # every step: pinned host positions -> device (H2D), `model(batch)` (the reference-facing forward, which
+    # also reads the device status word), adk_se3_step through the C ABI, new positions -> pinned host (D2H).
     h_out = torch.empty(N, 3, dtype=torch.float32).pin_memory()
     h_pos.copy_(pos.cpu())
+    model(batch)  # warm the eager path
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        pos.copy_(h_pos, non_blocking=True)
+        batch.pos.copy_(h_pos, non_blocking=True)
         if int(run_steps.done) % total_steps == 0:
             step.zero_()
-        graph.replay()
+        s_tr, s_rot = model(batch)
+        _cabi.call("adk_se3_step", dev, _cabi.ptr(batch.pos), _cabi.ptr(plan.cell_f32), _cabi.ptr(plan.atom_off),
+                   _cabi.ptr(tags), _cabi.ptr(fixed), _cabi.ptr(s_tr), _cabi.ptr(s_rot), _cabi.ptr(sched),
+                   _cabi.ptr(step), S_per, _cabi.ptr(max_upd))
         run_steps.done += 1
-        h_out.copy_(pos, non_blocking=True)
+        h_out.copy_(batch.pos, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()  # the caller reads the result before the next step
         h_pos.copy_(h_out)
     f1.record()
