@@ -100,12 +100,14 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     const bool has_vec = P.vec_in != nullptr;
 
     // ---- stage the weight slice: 16-byte chunks (8 features) of wt_split[plane][k][g*F + f0 ..] ----
+    // cp.async (LDGSTS): all copies of the CTA are in flight at once, no register staging
     for (int i = threadIdx.x; i < 2 * R * 12; i += MM_THREADS) {
         const int plane = i / (R * 12), rem = i - plane * (R * 12);
         const int k = rem / 12, ch = rem - k * 12;          // ch = g * 4 + chunk
         const int g = ch >> 2, c4 = ch & 3;
-        const uint4 v = *reinterpret_cast<const uint4*>(P.wt_split + ((size_t)plane * R + k) * 3 * F + g * F + f0 + c4 * 8);
-        *reinterpret_cast<uint4*>((plane ? s_wl : s_wh) + (size_t)k * MM_WROW + ch * 16) = v;
+        const __half* src = P.wt_split + ((size_t)plane * R + k) * 3 * F + g * F + f0 + c4 * 8;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared((plane ? s_wl : s_wh) + (size_t)k * MM_WROW + ch * 16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
     for (int k = threadIdx.x; k < R; k += MM_THREADS) s_mu[k] = P.rbf_offset[k];
     if (threadIdx.x < 96) {
@@ -118,10 +120,19 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
         const int pos = (lane >> 4) * 16 + ((lane >> 1) & 3) * 4 + ((lane >> 3) & 1) * 2 + (lane & 1);
         for (int seg = warp; seg < n * 3; seg += MM_WARPS) {
             const int j = seg / 3, g = seg - j * 3;
-            s_xh[j * MM_SRC_STRIDE + g * 32 + pos] = P.xh[(size_t)(a0 + j) * 3 * F + g * F + f0 + lane];
-            if (has_vec) s_vec[j * MM_SRC_STRIDE + g * 32 + pos] = P.vec_in[(size_t)(a0 + j) * 3 * F + g * F + f0 + lane];
+            const size_t go = (size_t)(a0 + j) * 3 * F + g * F + f0 + lane;
+            const uint32_t so = (uint32_t)(j * MM_SRC_STRIDE + g * 32 + pos) * 4u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(s_xh) + so),
+                         "l"(P.xh + go)
+                         : "memory");
+            if (has_vec)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(s_vec) + so),
+                             "l"(P.vec_in + go)
+                             : "memory");
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int qr = lane >> 2, qt = lane & 3;   // fragment coordinates: row group, column pair
@@ -143,22 +154,30 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
 #pragma unroll
             for (int c = 0; c < 3; ++c) dva[c][nt][0] = dva[c][nt][1] = 0.f;
         }
+        // this lane's two outputs of the row-end write (see the reduce-scatter below): fetch the residual x early
+        const int blk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        float2 x_res[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int o = 2 * blk + w;
+            if (o < 4) x_res[w] = *reinterpret_cast<const float2*>(P.x_io + (size_t)t * F + f0 + o * 8 + 2 * qt);
+        }
         // software pipeline: the CSR records of the next chunk are fetched while this one is processed
         int nx_src = 0;
         float4 nx_geo = make_float4(0.f, 0.f, 0.f, 0.f);
         if (lane < min(16, deg)) {
-            nx_src = P.e_src[start + lane] - a0;
+            nx_src = P.e_src[start + lane];   // global index; made local at use so the load stays in flight
             nx_geo = P.e_geo[start + lane];
         }
         for (int e0 = 0; e0 < deg; e0 += 16) {
             const int cnt = min(16, deg - e0);
             // lanes 0..15 own one edge record each
-            const int my_src = nx_src;
+            const int my_src = nx_src - a0;
             const float4 my_geo = nx_geo;
             int my_klo = 0;
             float my_s = 0.f, my_env = 0.f;
             if (lane < min(16, deg - e0 - 16)) {
-                nx_src = P.e_src[start + e0 + 16 + lane] - a0;
+                nx_src = P.e_src[start + e0 + 16 + lane];
                 nx_geo = P.e_geo[start + e0 + 16 + lane];
             }
             if (lane < cnt) {
@@ -315,18 +334,14 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
             }
         }
         // this lane owns outputs o0 = 2 * blk and o0 + 1 (o < 4: dx of n-tile o; else dvec[(o-4)/4] of n-tile (o-4)%4)
-        const int blk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
             const int o = 2 * blk + w;
             const float rx0 = v4[2 * w], rx1 = v4[2 * w + 1];
             if (o < 4) {
                 const int fo = f0 + o * 8 + 2 * qt;
-                float2* xo = reinterpret_cast<float2*>(P.x_io + (size_t)t * F + fo);
-                float2 xv = *xo;
-                xv.x = (xv.x + rx0) * 0.70710678118654752440f;
-                xv.y = (xv.y + rx1) * 0.70710678118654752440f;
-                *xo = xv;
+                *reinterpret_cast<float2*>(P.x_io + (size_t)t * F + fo) =
+                    make_float2((x_res[w].x + rx0) * 0.70710678118654752440f, (x_res[w].y + rx1) * 0.70710678118654752440f);
             } else {
                 const int c = (o - 4) >> 2, nt = (o - 4) & 3;
                 const int fo = f0 + nt * 8 + 2 * qt;
