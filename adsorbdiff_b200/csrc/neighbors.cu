@@ -79,12 +79,27 @@ __device__ int prune_to_k(uint32_t* cd2, uint32_t* cid, int cnt, int k) {
     const int lane = adk::lane_id();
     // k-th smallest value: largest T with count(v < T) < k, built bit by bit (d2 > 0 => uint order).
     uint32_t T = 0;
-    for (int bit = 30; bit >= 0; --bit) {
-        uint32_t trial = T | (1u << bit);
-        int c = 0;
-        for (int p = lane; p < cnt; p += 32) c += (cd2[p] < trial) ? 1 : 0;
-        c = __reduce_add_sync(ADK_FULL_MASK, c);
-        if (c < k) T = trial;
+    if (cnt <= 32 * 10) {
+        // common case (~280 in-cutoff candidates at 12 A): keys live in registers for the 31 bit steps
+        uint32_t v[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) v[i] = (lane + 32 * i < cnt) ? cd2[lane + 32 * i] : 0xffffffffu;
+        for (int bit = 30; bit >= 0; --bit) {
+            const uint32_t trial = T | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) c += (v[i] < trial) ? 1 : 0;
+            c = __reduce_add_sync(ADK_FULL_MASK, c);
+            if (c < k) T = trial;
+        }
+    } else {
+        for (int bit = 30; bit >= 0; --bit) {
+            uint32_t trial = T | (1u << bit);
+            int c = 0;
+            for (int p = lane; p < cnt; p += 32) c += (cd2[p] < trial) ? 1 : 0;
+            c = __reduce_add_sync(ADK_FULL_MASK, c);
+            if (c < k) T = trial;
+        }
     }
     int n_less = 0;
     for (int p = lane; p < cnt; p += 32) n_less += (cd2[p] < T) ? 1 : 0;
@@ -161,6 +176,42 @@ __global__ void __launch_bounds__(NB_THREADS) neighbors_kernel(NbParams P) {
     for (int i = warp; i < n; i += NB_WARPS) {
         const float pix = s_pos[3 * i], piy = s_pos[3 * i + 1], piz = s_pos[3 * i + 2];
         int cnt = 0;
+        if (C <= 96) {
+            // common case (75 images for an OC20 slab at 12 A): a lane keeps the offsets of its <= 3 images in
+            // registers and the warp walks the source atoms; enumeration order is still (j, image) ascending.
+            float ox[3], oy[3], oz[3];
+#pragma unroll
+            for (int sl = 0; sl < 3; ++sl) {
+                const int cc = min(lane + 32 * sl, C - 1);
+                ox[sl] = s_off[cc]; oy[sl] = s_off[C + cc]; oz[sl] = s_off[2 * C + cc];
+            }
+            for (int j = 0; j < n; ++j) {
+                const float pjx = s_pos[3 * j], pjy = s_pos[3 * j + 1], pjz = s_pos[3 * j + 2];
+#pragma unroll
+                for (int sl = 0; sl < 3; ++sl) {
+                    if (32 * sl < C) {  // warp-uniform
+                        const int c = lane + 32 * sl;
+                        const float p2x = __fadd_rn(pjx, ox[sl]), p2y = __fadd_rn(pjy, oy[sl]), p2z = __fadd_rn(pjz, oz[sl]);
+                        const float dx = __fsub_rn(pix, p2x), dy = __fsub_rn(piy, p2y), dz = __fsub_rn(piz, p2z);
+                        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                        const bool ok = (c < C) && (d2 <= P.cutoff2) && (d2 > 0.0001f);
+                        const unsigned m = __ballot_sync(ADK_FULL_MASK, ok);
+                        if (m) {
+                            if (cnt + 32 > CAND_MAX) {
+                                __syncwarp();
+                                if (cnt > k) cnt = prune_to_k(cd2, cid, cnt, k);
+                            }
+                            if (ok) {
+                                const int p = cnt + __popc(m & adk::lanemask_lt());
+                                cd2[p] = __float_as_uint(d2);
+                                cid[p] = ((uint32_t)j << 16) | (uint32_t)c;
+                            }
+                            cnt += __popc(m);
+                        }
+                    }
+                }
+            }
+        } else {
         int j = 0, c = lane;  // (j, c) of this lane's pair, advanced incrementally
         while (c >= C) { c -= C; ++j; }
         for (int base = 0; base < total; base += 32) {
@@ -189,6 +240,7 @@ __global__ void __launch_bounds__(NB_THREADS) neighbors_kernel(NbParams P) {
             }
             c += 32;
             while (c >= C) { c -= C; ++j; }
+        }
         }
         __syncwarp();
         if (cnt > k) cnt = prune_to_k(cd2, cid, cnt, k);
