@@ -51,7 +51,7 @@ struct MmParams {
     int F, R, n_max;
     float inv_cutoff, coeff, env_a, env_b, env_c;
     int env_p;
-    float acc_scale;
+    float acc_scale, coeff_sqrt;
     float* x_io;
     float* vec_out;
     __half* vsplit;        // optional fp16x2 planes of vec_out, [2][vsplit_rows][F] (row = atom * 3 + xyz)
@@ -83,6 +83,12 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
     const __half2 ll = __floats2half2_rn(v0 - back.x, v1 - back.y);
     hi = *reinterpret_cast<const uint32_t*>(&hh);
     lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) {
@@ -141,8 +147,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     // ldmatrix.x4.trans lane address: matrices (k 0-7 | k 8-15) x (n-tile nt | nt+1)
     const int lm_krow = (lane & 7) + ((lane >> 3) & 1) * 8;
     const int lm_ntile = lane >> 4;
-    const float inv_sqrt_3 = 0.57735026918962576451f;
-    const float inv_sqrt_h = 1.0f / sqrtf((float)F);
+    const float sqrt_3 = 1.7320508075688772f;
+    const float inv_sqrt_h = 0.57735026918962576451f / sqrtf((float)F);   // includes the 1/sqrt(3) of x_ij2
 
     for (int tl = warp; tl < n; tl += MM_WARPS) {
         const int t = a0 + tl;
@@ -211,11 +217,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float mu0 = s_mu[k0 + 8 * h], mu1 = s_mu[k0 + 8 * h + 1];
-                    float d;
-                    d = s_a - mu0; g8[4 * h + 0] = env_a * __expf(P.coeff * d * d);
-                    d = s_a - mu1; g8[4 * h + 1] = env_a * __expf(P.coeff * d * d);
-                    d = s_b - mu0; g8[4 * h + 2] = env_b * __expf(P.coeff * d * d);
-                    d = s_b - mu1; g8[4 * h + 3] = env_b * __expf(P.coeff * d * d);
+                    float t;
+                    t = (s_a - mu0) * P.coeff_sqrt; g8[4 * h + 0] = env_a * ex2_approx(-t * t);
+                    t = (s_a - mu1) * P.coeff_sqrt; g8[4 * h + 1] = env_a * ex2_approx(-t * t);
+                    t = (s_b - mu0) * P.coeff_sqrt; g8[4 * h + 2] = env_b * ex2_approx(-t * t);
+                    t = (s_b - mu1) * P.coeff_sqrt; g8[4 * h + 3] = env_b * ex2_approx(-t * t);
                 }
                 uint32_t ah[4], al[4];
                 split_pair(g8[0], g8[1], ah[0], al[0]);   // (row qr,     k 2t..2t+1)
@@ -246,9 +252,10 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
             for (int hrow = 0; hrow < 2; ++hrow) {
                 const int er = qr + 8 * hrow;
                 const int src = __shfl_sync(ADK_FULL_MASK, my_src, er);
-                const float rx = __shfl_sync(ADK_FULL_MASK, my_geo.y, er);
-                const float ry = __shfl_sync(ADK_FULL_MASK, my_geo.z, er);
-                const float rz = __shfl_sync(ADK_FULL_MASK, my_geo.w, er);
+                // r_hat carries sqrt(3); the row-end scale carries 1/sqrt(3) for the whole dvec sum
+                const float rx = __shfl_sync(ADK_FULL_MASK, my_geo.y, er) * sqrt_3;
+                const float ry = __shfl_sync(ADK_FULL_MASK, my_geo.z, er) * sqrt_3;
+                const float rz = __shfl_sync(ADK_FULL_MASK, my_geo.w, er) * sqrt_3;
                 if (er < cnt) {
                     const float* xs = s_xh + (size_t)src * MM_SRC_STRIDE + qt * 4;
                     const float* vs = s_vec + (size_t)src * MM_SRC_STRIDE + qt * 4;
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
                             dva[0][nt][h] = fmaf(m3, rx, dva[0][nt][h]);
                             dva[1][nt][h] = fmaf(m3, ry, dva[1][nt][h]);
                             dva[2][nt][h] = fmaf(m3, rz, dva[2][nt][h]);
-                            m2[2 * nt + h] = h2[2 * nt + h] * r2 * inv_sqrt_3;
+                            m2[2 * nt + h] = h2[2 * nt + h] * r2;
                         }
                     if (has_vec) {
 #pragma unroll
@@ -425,6 +432,7 @@ extern "C" int adk_message_mma(const int32_t* atom_off, int B, int n_max, const 
     P.env_b = (float)(p * (p + 2));
     P.env_c = (float)(-p * (p + 1) / 2);
     P.acc_scale = (1.0f + comp) / (MM_RBF_SCALE * w_scale);
+    P.coeff_sqrt = (float)(sqrt(0.5 * 1.4426950408889634) / spacing);  // exp(coeff d^2) = 2^-(coeff_sqrt d)^2
     P.x_io = x_io; P.vec_out = vec_out;
     P.vsplit = reinterpret_cast<__half*>(vec_split); P.vsplit_plane = split_rows * (int64_t)F;
     P.vsplit_scale = split_scale; P.status = status;
