@@ -64,10 +64,12 @@ __host__ __device__ inline size_t mm_smem_bytes(int R, int n_max) {
     return 2 * (size_t)R * MM_WROW + sizeof(float) * ((size_t)R + 96) + sizeof(float) * (size_t)n_max * 2 * MM_SRC_STRIDE + 64;
 }
 
+// the column offset is an immediate of the instruction: one address register per (k-step, plane) instead of six
+template <int OFF>
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4+%5];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                 : "r"(addr));
+                 : "r"(addr), "n"(OFF));
 }
 __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -75,6 +77,14 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
         "{%0, %1, %2, %3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// first product of a chunk: C = 0 comes from the zero register, the accumulators need no clearing
+__device__ __forceinline__ void mma16816_z(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%10, %10, %10, %10};"
+        : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.0f));
 }
 // two scaled fp32 values -> packed fp16 hi pair and lo pair
 __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
@@ -147,6 +157,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     // ldmatrix.x4.trans lane address: matrices (k 0-7 | k 8-15) x (n-tile nt | nt+1)
     const int lm_krow = (lane & 7) + ((lane >> 3) & 1) * 8;
     const int lm_ntile = lane >> 4;
+    const uint32_t lm_base_hi = wh_base + (uint32_t)lm_krow * MM_WROW + (uint32_t)lm_ntile * 16;
+    const uint32_t lm_plane = wl_base - wh_base;
     const float sqrt_3 = 1.7320508075688772f;
     const float inv_sqrt_h = 0.57735026918962576451f / sqrtf((float)F);   // includes the 1/sqrt(3) of x_ij2
 
@@ -188,8 +200,14 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
             }
             if (lane < cnt) {
                 my_s = my_geo.x * P.inv_cutoff;
-                float sp = my_s;
-                for (int q = 1; q < P.env_p; ++q) sp *= my_s;
+                float sp;
+                if (P.env_p == 5) {           // the shipped configuration: s^5 in three multiplies, no loop
+                    const float s2 = my_s * my_s;
+                    sp = s2 * s2 * my_s;
+                } else {
+                    sp = my_s;
+                    for (int q = 1; q < P.env_p; ++q) sp *= my_s;
+                }
                 float env = 1.0f + P.env_a * sp;
                 sp *= my_s; env += P.env_b * sp;
                 sp *= my_s; env += P.env_c * sp;
@@ -207,10 +225,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
             const float env_a = __shfl_sync(ADK_FULL_MASK, my_env, qr), env_b = __shfl_sync(ADK_FULL_MASK, my_env, qr + 8);
 
             float acc[12][4];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-
-            for (int ks = 0; ks < nks; ++ks) {
+            {   // k-step 0 (every chunk has one): its first product initialises the accumulators
+                const int ks = 0;
                 const int k0 = kbase + ks * 16 + 2 * qt;
                 // A fragment: rbf values (already scaled by MM_RBF_SCALE through env), split into hi / lo
                 float g8[8];
@@ -228,15 +244,73 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
                 split_pair(g8[2], g8[3], ah[1], al[1]);   // (row qr + 8, k 2t..2t+1)
                 split_pair(g8[4], g8[5], ah[2], al[2]);   // (row qr,     k 2t+8..)
                 split_pair(g8[6], g8[7], ah[3], al[3]);   // (row qr + 8, k 2t+8..)
-                const uint32_t row_off = (uint32_t)(kbase + ks * 16 + lm_krow) * MM_WROW;
+                const uint32_t a_hi = lm_base_hi + (uint32_t)(kbase + ks * 16) * MM_WROW, a_lo = a_hi + lm_plane;
 #pragma unroll
                 for (int p4 = 0; p4 < 3; ++p4) {           // group g = p4: its four n-tiles, two ldmatrix.x4 per plane
-                    const uint32_t col_a = (uint32_t)(p4 * 64 + lm_ntile * 16), col_b = col_a + 32;
                     uint32_t bh[8], bl[8];
-                    ldmatrix_x4_trans(wh_base + row_off + col_a, bh[0], bh[1], bh[2], bh[3]);
-                    ldmatrix_x4_trans(wh_base + row_off + col_b, bh[4], bh[5], bh[6], bh[7]);
-                    ldmatrix_x4_trans(wl_base + row_off + col_a, bl[0], bl[1], bl[2], bl[3]);
-                    ldmatrix_x4_trans(wl_base + row_off + col_b, bl[4], bl[5], bl[6], bl[7]);
+                    if (p4 == 0) {
+                        ldmatrix_x4_trans<0>(a_hi, bh[0], bh[1], bh[2], bh[3]);
+                        ldmatrix_x4_trans<32>(a_hi, bh[4], bh[5], bh[6], bh[7]);
+                        ldmatrix_x4_trans<0>(a_lo, bl[0], bl[1], bl[2], bl[3]);
+                        ldmatrix_x4_trans<32>(a_lo, bl[4], bl[5], bl[6], bl[7]);
+                    } else if (p4 == 1) {
+                        ldmatrix_x4_trans<64>(a_hi, bh[0], bh[1], bh[2], bh[3]);
+                        ldmatrix_x4_trans<96>(a_hi, bh[4], bh[5], bh[6], bh[7]);
+                        ldmatrix_x4_trans<64>(a_lo, bl[0], bl[1], bl[2], bl[3]);
+                        ldmatrix_x4_trans<96>(a_lo, bl[4], bl[5], bl[6], bl[7]);
+                    } else {
+                        ldmatrix_x4_trans<128>(a_hi, bh[0], bh[1], bh[2], bh[3]);
+                        ldmatrix_x4_trans<160>(a_hi, bh[4], bh[5], bh[6], bh[7]);
+                        ldmatrix_x4_trans<128>(a_lo, bl[0], bl[1], bl[2], bl[3]);
+                        ldmatrix_x4_trans<160>(a_lo, bl[4], bl[5], bl[6], bl[7]);
+                    }
+                    // pass-major order: four independent accumulators between dependent MMAs
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) mma16816_z(acc[4 * p4 + nt], ah, bl[2 * nt], bl[2 * nt + 1]);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) mma16816(acc[4 * p4 + nt], al, bh[2 * nt], bh[2 * nt + 1]);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) mma16816(acc[4 * p4 + nt], ah, bh[2 * nt], bh[2 * nt + 1]);
+                }
+            }
+            for (int ks = 1; ks < nks; ++ks) {
+                const int k0 = kbase + ks * 16 + 2 * qt;
+                // A fragment: rbf values (already scaled by MM_RBF_SCALE through env), split into hi / lo
+                float g8[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float mu0 = s_mu[k0 + 8 * h], mu1 = s_mu[k0 + 8 * h + 1];
+                    float t;
+                    t = (s_a - mu0) * P.coeff_sqrt; g8[4 * h + 0] = env_a * ex2_approx(-t * t);
+                    t = (s_a - mu1) * P.coeff_sqrt; g8[4 * h + 1] = env_a * ex2_approx(-t * t);
+                    t = (s_b - mu0) * P.coeff_sqrt; g8[4 * h + 2] = env_b * ex2_approx(-t * t);
+                    t = (s_b - mu1) * P.coeff_sqrt; g8[4 * h + 3] = env_b * ex2_approx(-t * t);
+                }
+                uint32_t ah[4], al[4];
+                split_pair(g8[0], g8[1], ah[0], al[0]);   // (row qr,     k 2t..2t+1)
+                split_pair(g8[2], g8[3], ah[1], al[1]);   // (row qr + 8, k 2t..2t+1)
+                split_pair(g8[4], g8[5], ah[2], al[2]);   // (row qr,     k 2t+8..)
+                split_pair(g8[6], g8[7], ah[3], al[3]);   // (row qr + 8, k 2t+8..)
+                const uint32_t a_hi = lm_base_hi + (uint32_t)(kbase + ks * 16) * MM_WROW, a_lo = a_hi + lm_plane;
+#pragma unroll
+                for (int p4 = 0; p4 < 3; ++p4) {           // group g = p4: its four n-tiles, two ldmatrix.x4 per plane
+                    uint32_t bh[8], bl[8];
+                    if (p4 == 0) {
+                        ldmatrix_x4_trans<0>(a_hi, bh[0], bh[1], bh[2], bh[3]);
+                        ldmatrix_x4_trans<32>(a_hi, bh[4], bh[5], bh[6], bh[7]);
+                        ldmatrix_x4_trans<0>(a_lo, bl[0], bl[1], bl[2], bl[3]);
+                        ldmatrix_x4_trans<32>(a_lo, bl[4], bl[5], bl[6], bl[7]);
+                    } else if (p4 == 1) {
+                        ldmatrix_x4_trans<64>(a_hi, bh[0], bh[1], bh[2], bh[3]);
+                        ldmatrix_x4_trans<96>(a_hi, bh[4], bh[5], bh[6], bh[7]);
+                        ldmatrix_x4_trans<64>(a_lo, bl[0], bl[1], bl[2], bl[3]);
+                        ldmatrix_x4_trans<96>(a_lo, bl[4], bl[5], bl[6], bl[7]);
+                    } else {
+                        ldmatrix_x4_trans<128>(a_hi, bh[0], bh[1], bh[2], bh[3]);
+                        ldmatrix_x4_trans<160>(a_hi, bh[4], bh[5], bh[6], bh[7]);
+                        ldmatrix_x4_trans<128>(a_lo, bl[0], bl[1], bl[2], bl[3]);
+                        ldmatrix_x4_trans<160>(a_lo, bl[4], bl[5], bl[6], bl[7]);
+                    }
                     // pass-major order: four independent accumulators between dependent MMAs
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) mma16816(acc[4 * p4 + nt], ah, bl[2 * nt], bl[2 * nt + 1]);
