@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     const float sqrt_3 = 1.7320508075688772f;
     const float inv_sqrt_h = 0.57735026918962576451f / sqrtf((float)F);   // includes the 1/sqrt(3) of x_ij2
 
-    for (int tl = warp; tl < n; tl += MM_WARPS) {
+    // gridDim.z > 1 (a handful of systems only): the target rows of a system are dealt to several CTAs
+    for (int tl = warp + MM_WARPS * blockIdx.z; tl < n; tl += MM_WARPS * gridDim.z) {
         const int t = a0 + tl;
         const int start = P.row_start[t], deg = P.row_deg[t];
         float dxa[4][2], dva[3][4][2];
@@ -510,7 +511,10 @@ extern "C" int adk_message_mma(const int32_t* atom_off, int B, int n_max, const 
     P.x_io = x_io; P.vec_out = vec_out;
     P.vsplit = reinterpret_cast<__half*>(vec_split); P.vsplit_plane = split_rows * (int64_t)F;
     P.vsplit_scale = split_scale; P.status = status;
-    message_mma_kernel<<<dim3(B, F / MM_SF), MM_THREADS, smem, adk::as_stream(stream)>>>(P);
+    // one CTA per (system, feature slice) fills the GPU from ~10 systems on; below that split the rows as well
+    int row_splits = 1;
+    while (row_splits < 4 && (long long)B * (F / MM_SF) * row_splits * 2 <= 160) row_splits *= 2;
+    message_mma_kernel<<<dim3(B, F / MM_SF, row_splits), MM_THREADS, smem, adk::as_stream(stream)>>>(P);
     ADK_LAUNCH_CHECK();
     return 0;
 }

@@ -18,8 +18,11 @@
 
 namespace {
 
-constexpr int NB_THREADS = 256;
-constexpr int NB_WARPS = NB_THREADS / 32;
+// Warps per CTA are a launch-time choice: 8 when there are enough systems to fill the GPU with several CTAs per
+// SM, up to 24 when a handful of systems must each finish quickly (single-placement sampling: the one CTA of a
+// system is on the critical path of every reverse step).
+constexpr int NB_WARPS_DEFAULT = 8;
+constexpr int NB_WARPS_MAX = 24;
 constexpr int CAND_MAX = 1024;  // per-warp candidate staging (pruned to k when it fills)
 
 struct NbParams {
@@ -45,13 +48,13 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(
 
 struct NbSmem {
     size_t pos, off, neg, cand_d2, cand_id, kept, kept_cnt, rev_cnt, row_start, misc, total;
-    __host__ __device__ NbSmem(int n_max, int C, int k) {
+    __host__ __device__ NbSmem(int n_max, int C, int k, int warps) {
         size_t o = 0;
         pos = o;       o = align16(o + sizeof(float) * 3 * n_max);
         off = o;       o = align16(o + sizeof(float) * 3 * C);
         neg = o;       o = align16(o + C);
-        cand_d2 = o;   o = align16(o + sizeof(uint32_t) * NB_WARPS * CAND_MAX);
-        cand_id = o;   o = align16(o + sizeof(uint32_t) * NB_WARPS * CAND_MAX);
+        cand_d2 = o;   o = align16(o + sizeof(uint32_t) * warps * CAND_MAX);
+        cand_id = o;   o = align16(o + sizeof(uint32_t) * warps * CAND_MAX);
         kept = o;      o = align16(o + sizeof(uint32_t) * (size_t)n_max * k);
         kept_cnt = o;  o = align16(o + sizeof(int) * n_max);
         rev_cnt = o;   o = align16(o + sizeof(int) * n_max);
@@ -128,7 +131,7 @@ __device__ int prune_to_k(uint32_t* cd2, uint32_t* cid, int cnt, int k) {
     return wp;
 }
 
-__global__ void __launch_bounds__(NB_THREADS) neighbors_kernel(NbParams P) {
+__global__ void __launch_bounds__(NB_WARPS_MAX * 32) neighbors_kernel(NbParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int a0 = P.atom_off[b];
@@ -136,7 +139,8 @@ __global__ void __launch_bounds__(NB_THREADS) neighbors_kernel(NbParams P) {
     const int n1 = 2 * P.rep1 + 1, n2 = 2 * P.rep2 + 1, n3 = 2 * P.rep3 + 1;
     const int C = n1 * n2 * n3;
     const int k = P.k;
-    NbSmem L(P.n_max, C, k);
+    const int NB_THREADS = blockDim.x, NB_WARPS = blockDim.x >> 5;
+    NbSmem L(P.n_max, C, k, NB_WARPS);
     float* s_pos = reinterpret_cast<float*>(smem_raw + L.pos);
     float* s_off = reinterpret_cast<float*>(smem_raw + L.off);  // [3][C]
     unsigned char* s_neg = smem_raw + L.neg;
@@ -443,13 +447,23 @@ __global__ void __launch_bounds__(256) export_edges_kernel(
     }
 }
 
+int nb_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
 }  // namespace
 
 extern "C" int64_t adk_neighbors_smem_bytes(int n_max, int num_images, int max_nbrs) {
     if (n_max <= 0 || n_max > ADK_MAX_ATOMS_PER_SYSTEM || num_images <= 0 || num_images > ADK_MAX_IMAGES ||
         max_nbrs <= 0 || max_nbrs > 256)
         return ADK_ERANGE;
-    NbSmem L(n_max, num_images, max_nbrs);
+    NbSmem L(n_max, num_images, max_nbrs, NB_WARPS_DEFAULT);
     if (L.total > 227 * 1024) return ADK_ERANGE;
     return (int64_t)L.total;
 }
@@ -470,7 +484,14 @@ extern "C" int adk_neighbors(const float* pos, const float* cell, const int32_t*
     P.cutoff2 = cutoff2; P.k = max_nbrs; P.n_max = n_max;
     P.row_start = row_start; P.row_deg = row_deg; P.e_src = e_src; P.e_tgt = e_tgt; P.e_geo = reinterpret_cast<float4*>(e_geo);
     P.kept_pack = kept_pack; P.kept_cnt = kept_cnt; P.sys_counts = sys_counts; P.status = status;
-    neighbors_kernel<<<B, NB_THREADS, (size_t)smem, adk::as_stream(stream)>>>(P);
+    // few systems: spend more warps per system (latency), as long as the candidate staging still fits
+    int warps = NB_WARPS_DEFAULT;
+    if (B < 2 * nb_num_sms()) {
+        warps = B < nb_num_sms() ? NB_WARPS_MAX : 16;
+        while (warps > NB_WARPS_DEFAULT && NbSmem(n_max, C, max_nbrs, warps).total > 227 * 1024) warps -= 4;
+        smem = (int64_t)NbSmem(n_max, C, max_nbrs, warps).total;
+    }
+    neighbors_kernel<<<B, warps * 32, (size_t)smem, adk::as_stream(stream)>>>(P);
     ADK_LAUNCH_CHECK();
     return 0;
 }
