@@ -95,7 +95,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = threadIdx.x; i < P.N; i += TC_THREADS) s_bias[i] = P.bias ? P.bias[i] : 0.0f;
 
     const int warp = adk::warp_id(), lane = adk::lane_id();
-    const int num_m = (P.M + TC_BM - 1) / TC_BM, num_n = P.N / TC_BN, num_k = P.K / TC_BK;
+    const int num_m = (P.M + TC_BM - 1) / TC_BM, num_n = (P.N + TC_BN - 1) / TC_BN, num_k = P.K / TC_BK;
     const int num_tiles = num_m * num_n;
 
     if (warp == 0 && lane == 0) {
@@ -223,6 +223,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int pc = 0; pc < TC_EPI_COLS / 16; ++pc) {
                 const int n = n0 + pc * 16;
+                if (n >= P.N) break;   // ragged last tile (N % 256 != 0): those accumulator columns are padding
                 float o[16];
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -358,7 +359,7 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
                              void* out_split, int64_t out_plane_rows, float out_split_scale, uint32_t* status,
                              void* stream) {
     if (!a_split || !w_split || M <= 0 || N <= 0 || K <= 0 || (!out_f32 && !out_split)) return ADK_EINVAL;
-    if (N % TC_BN != 0 || K % TC_BK != 0 || a_plane_rows < M || a_plane_rows % TC_BM != 0) return ADK_EINVAL;
+    if (N % 16 != 0 || K % TC_BK != 0 || a_plane_rows < M || a_plane_rows % TC_BM != 0) return ADK_EINVAL;
     if (out_f32 && ((ldc & 3) || (reinterpret_cast<uintptr_t>(out_f32) & 15))) return ADK_EINVAL;
     if (out_split && out_plane_rows < M) return ADK_EINVAL;
     alignas(64) CUtensorMap tmA, tmW;
@@ -374,7 +375,7 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     P.out_split_plane = out_plane_rows * (int64_t)N;
     P.out_split_scale = out_split_scale;
     P.status = status;
-    const int tiles = ((M + TC_BM - 1) / TC_BM) * (N / TC_BN);
+    const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + TC_BN - 1) / TC_BN);
     const int grid = tiles < adk::tc::g_num_sms ? tiles : adk::tc::g_num_sms;
     if (N > TC_MAX_N) return ADK_ERANGE;
     cudaStream_t st = adk::as_stream(stream);

@@ -366,7 +366,16 @@ class PaiNN(nn.Module):
         for h in heads:
             b0, b1 = h.output_network
             out += [b0.vec1_proj, b0.vec2_proj, b0.update_net[0], b0.update_net[2], b1.vec1_proj, b1.update_net[0]]
-        return [l for l in out if l.weight.shape[0] % 128 == 0 and l.weight.shape[1] % 64 == 0]
+        return [l for l in out if self._tc_shape_ok(l)]
+
+    @staticmethod
+    def _tc_shape_ok(lin) -> bool:
+        """adk_linear_tc takes N % 16 == 0 and K % 64 == 0; anything else (the 2- and 1-wide last layers of the
+        heads, odd widths) runs on the exact-fp32 SIMT kernel."""
+        return lin.weight.shape[0] % 16 == 0 and lin.weight.shape[1] % 64 == 0
+
+    def _tc_ok(self, lin) -> bool:
+        return self.gemm == "tc" and self._tc_shape_ok(lin)
 
     def _resplit_weights(self, p) -> None:
         """fp16x2 planes of all tensor-core weights, rebuilt at the start of EVERY forward in one launch
@@ -407,38 +416,32 @@ class PaiNN(nn.Module):
     def _mlp2(self, p, A, lda, M, K, lin0, lin1, out, ldc, presplit=False):
         """out = lin1(ssilu(lin0(A))): the two-layer MLP shape shared by x_proj, xvec_proj and update_net.
         `presplit`: the producer kernel already wrote the fp16x2 planes of A into p.sp_x."""
-        if self.gemm == "tc" and lin1.weight.shape[0] % 256 == 0:
+        if self._tc_ok(lin0):
             rows = p.rows_n
             if not presplit:
                 self._split(p, A, lda, M, K, p.sp_x, rows)
-            self._linear_tc(p, p.sp_x, rows, M, lin0, _cabi.ACT_SSILU, out_split=p.sp_h, out_rows=rows)
-            self._linear_tc(p, p.sp_h, rows, M, lin1, _cabi.ACT_NONE, out_f32=out, ldc=ldc)
-        elif self.gemm == "tc":
-            rows = p.rows_n
-            if not presplit:
-                self._split(p, A, lda, M, K, p.sp_x, rows)
-            self._linear_tc(p, p.sp_x, rows, M, lin0, _cabi.ACT_SSILU, out_f32=p.h1, ldc=lin0.weight.shape[0])
-            self._linear(p, p.h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
+            if self._tc_ok(lin1):
+                self._linear_tc(p, p.sp_x, rows, M, lin0, _cabi.ACT_SSILU, out_split=p.sp_h, out_rows=rows)
+                self._linear_tc(p, p.sp_h, rows, M, lin1, _cabi.ACT_NONE, out_f32=out, ldc=ldc)
+            else:
+                self._linear_tc(p, p.sp_x, rows, M, lin0, _cabi.ACT_SSILU, out_f32=p.h1, ldc=lin0.weight.shape[0])
+                self._linear(p, p.h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
         else:
+            assert not presplit, "producer must hand an fp32 operand to the SIMT path"
             self._linear(p, A, lda, lin0, M, _cabi.ACT_SSILU, p.h1, lin0.weight.shape[0])
             self._linear(p, p.h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
 
     def _vec_linear(self, p, vec, K, lins_outs, presplit=False):
         """vec-wise bias-free projections of [3N, K] (vec_proj, vec1_proj, vec2_proj); one split feeds all."""
         M = 3 * p.N
-        if self.gemm == "tc":
-            if not presplit:
-                self._split(p, vec, K, M, K, p.sp_v, p.rows_3n, self.V_SCALE)
-            for lin, out in lins_outs:
-                n_out = lin.weight.shape[0]
-                if n_out % 256 == 0:
-                    self._linear_tc(p, p.sp_v, p.rows_3n, M, lin, _cabi.ACT_NONE, out_f32=out, ldc=n_out,
-                                    a_scale=self.V_SCALE)
-                else:
-                    self._linear(p, vec, K, lin, M, _cabi.ACT_NONE, out, n_out)
-        else:
-            for lin, out in lins_outs:
-                self._linear(p, vec, K, lin, M, _cabi.ACT_NONE, out, lin.weight.shape[0])
+        if not presplit and any(self._tc_ok(lin) for lin, _ in lins_outs):
+            self._split(p, vec, K, M, K, p.sp_v, p.rows_3n, self.V_SCALE)
+        for lin, out in lins_outs:
+            n_out = lin.weight.shape[0]
+            if self._tc_ok(lin):
+                self._linear_tc(p, p.sp_v, p.rows_3n, M, lin, _cabi.ACT_NONE, out_f32=out, ldc=n_out, a_scale=self.V_SCALE)
+            else:
+                self._linear(p, vec, K, lin, M, _cabi.ACT_NONE, out, n_out)
 
     def _head(self, p: _Plan, head: _OutputParams, x, vec, out, presplit: bool) -> None:
         N, F = p.N, self.hidden_channels
@@ -447,13 +450,14 @@ class PaiNN(nn.Module):
         dev = p.device
         # block 0: F -> H
         self._vec_linear(p, vec, F, [(b0.vec1_proj, p.v1p), (b0.vec2_proj, p.v2p)], presplit=presplit)
-        tc = self.gemm == "tc"
+        tc = self._tc_ok(b0.update_net[0])
         call("adk_head_prep", dev, ptr(x), ptr(p.v1p), N, F, None if tc else ptr(p.cat), ptr(p.sp_x) if tc else None,
              p.rows_n, self.A_SCALE, ptr(p.status))
         self._mlp2(p, p.cat, 2 * F, N, 2 * F, b0.update_net[0], b0.update_net[2], p.xn, F, presplit=tc)  # (s|g)
         call("adk_head_gate", dev, ptr(p.xn), ptr(p.v2p), N, H, ptr(p.hx), ptr(p.hv))
         # block 1: H -> 1
         self._vec_linear(p, p.hv, H, [(b1.vec1_proj, p.v1p), (b1.vec2_proj, p.v2p2)])
+        tc = self._tc_ok(b1.update_net[0])
         call("adk_head_prep", dev, ptr(p.hx), ptr(p.v1p), N, H, None if tc else ptr(p.cat), ptr(p.sp_x) if tc else None,
              p.rows_n, self.A_SCALE, ptr(p.status))
         self._mlp2(p, p.cat, 2 * H, N, 2 * H, b1.update_net[0], b1.update_net[2], p.ho2, 2, presplit=tc)
@@ -471,7 +475,7 @@ class PaiNN(nn.Module):
         cur = 0
         for l in range(self.num_layers):
             m, u = self.message_layers[l], self.update_layers[l]
-            tc = self.gemm == "tc"
+            tc = self._tc_ok(m.x_proj[0])
             call("adk_layernorm", dev, ptr(p.x), ptr(m.x_layernorm.weight), ptr(m.x_layernorm.bias), N, F,
                  float(m.x_layernorm.eps), None if tc else ptr(p.xn), ptr(p.sp_x) if tc else None, p.rows_n,
                  self.A_SCALE, ptr(p.status))
@@ -487,8 +491,8 @@ class PaiNN(nn.Module):
                      ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wt),
                      self.W_SCALE, ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R,
                      float(self.cutoff), self.radial_basis.exponent, float(self.msg_comp), ptr(p.x), ptr(vout),
-                     ptr(p.sp_v) if tc else None, p.rows_3n, self.V_SCALE, ptr(p.status))
-                vec_presplit = tc
+                     ptr(p.sp_v) if self._tc_ok(u.vec_proj) else None, p.rows_3n, self.V_SCALE, ptr(p.status))
+                vec_presplit = self._tc_ok(u.vec_proj)
             elif self.msg == "tc" and F == 512 and R == 128:
                 wr = self._wsplit(p, m.rbf_proj)
                 call("adk_message_tc", dev, ptr(p.atom_off), p.B, ptr(p.sys_counts), ptr(p.row_deg), ptr(p.e_src),
@@ -505,6 +509,7 @@ class PaiNN(nn.Module):
             if trace is not None:
                 trace[f"msg{l}.x"], trace[f"msg{l}.vec"] = p.x.clone(), vec.clone()
             self._vec_linear(p, vec, F, [(u.vec_proj, p.vp)], presplit=vec_presplit)
+            tc = self._tc_ok(u.xvec_proj[0])
             call("adk_update_prep", dev, ptr(p.x), ptr(p.vp), N, F, ptr(p.dot), None if tc else ptr(p.cat),
                  ptr(p.sp_x) if tc else None, p.rows_n, self.A_SCALE, ptr(p.status))
             self._mlp2(p, p.cat, 2 * F, N, 2 * F, u.xvec_proj[0], u.xvec_proj[2], p.xh, 3 * F, presplit=tc)

@@ -124,7 +124,7 @@ int adk_linear(const float* A, int64_t lda, const float* W, const float* bias, i
  * adk_split_f16: src fp32 [M][K] (row stride ld) -> dst fp16 [2][plane_rows][K]; rows >= M untouched.
  *   ADK_STATUS_F16_OVERFLOW is OR-ed into *status if |s*x| > 65504.
  * adk_linear_tc: C = act(acc_scale * A.W^T + bias), A = a_split [2][a_plane_rows][K] (a_plane_rows a
- *   multiple of 128, >= M), W = w_split [2][N][K]; N % 256 == 0, K % 64 == 0; acc_scale = 1/(s_A*s_W).
+ *   multiple of 128, >= M), W = w_split [2][N][K]; N % 16 == 0 (tiles are 256 wide; a ragged last tile is masked), K % 64 == 0; acc_scale = 1/(s_A*s_W).
  *   Outputs: out_f32 [M][ldc] and/or out_split [2][out_plane_rows][N] (scaled by out_split_scale),
  *   either may be NULL (not both).
  */
