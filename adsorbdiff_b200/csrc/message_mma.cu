@@ -322,6 +322,20 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
                 }
             }
 
+            // rbfh = acc * scale + bias for both fragment rows at once: the bias is read from shared memory once per
+            // chunk (it was 14 % of the kernel's shared-memory wavefronts when each row block re-read it)
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                    const float4 bq = *reinterpret_cast<const float4*>(s_bias + g * 32 + np * 16 + qt * 4);
+                    float* a0p = acc[4 * g + 2 * np];
+                    float* a1p = acc[4 * g + 2 * np + 1];
+                    a0p[0] = fmaf(a0p[0], P.acc_scale, bq.x); a0p[2] = fmaf(a0p[2], P.acc_scale, bq.x);
+                    a0p[1] = fmaf(a0p[1], P.acc_scale, bq.y); a0p[3] = fmaf(a0p[3], P.acc_scale, bq.y);
+                    a1p[0] = fmaf(a1p[0], P.acc_scale, bq.z); a1p[2] = fmaf(a1p[2], P.acc_scale, bq.z);
+                    a1p[1] = fmaf(a1p[1], P.acc_scale, bq.w); a1p[3] = fmaf(a1p[3], P.acc_scale, bq.w);
+                }
             // messages of this lane's two edges (rows qr, qr + 8); acc[g * 4 + nt] = {row qr: c0 c1, row qr+8: c2 c3}
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
@@ -341,20 +355,12 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
                     *reinterpret_cast<float4*>(h2 + 4) = *reinterpret_cast<const float4*>(xs + 48);
                     *reinterpret_cast<float4*>(h3) = *reinterpret_cast<const float4*>(xs + 64);
                     *reinterpret_cast<float4*>(h3 + 4) = *reinterpret_cast<const float4*>(xs + 80);
-                    float m2[8], b1[8], b2[8], b3[8];
-                    *reinterpret_cast<float4*>(b1) = *reinterpret_cast<const float4*>(s_bias + qt * 4);
-                    *reinterpret_cast<float4*>(b1 + 4) = *reinterpret_cast<const float4*>(s_bias + qt * 4 + 16);
-                    *reinterpret_cast<float4*>(b2) = *reinterpret_cast<const float4*>(s_bias + 32 + qt * 4);
-                    *reinterpret_cast<float4*>(b2 + 4) = *reinterpret_cast<const float4*>(s_bias + 32 + qt * 4 + 16);
-                    *reinterpret_cast<float4*>(b3) = *reinterpret_cast<const float4*>(s_bias + 64 + qt * 4);
-                    *reinterpret_cast<float4*>(b3 + 4) = *reinterpret_cast<const float4*>(s_bias + 64 + qt * 4 + 16);
+                    float m2[8];
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const float r1 = fmaf(acc[nt][2 * hrow + h], P.acc_scale, b1[2 * nt + h]);
-                            const float r2 = fmaf(acc[4 + nt][2 * hrow + h], P.acc_scale, b2[2 * nt + h]);
-                            const float r3 = fmaf(acc[8 + nt][2 * hrow + h], P.acc_scale, b3[2 * nt + h]);
+                            const float r1 = acc[nt][2 * hrow + h], r2 = acc[4 + nt][2 * hrow + h], r3 = acc[8 + nt][2 * hrow + h];
                             dxa[nt][h] = fmaf(h1[2 * nt + h], r1, dxa[nt][h]);
                             const float m3 = h3[2 * nt + h] * r3;
                             dva[0][nt][h] = fmaf(m3, rx, dva[0][nt][h]);
