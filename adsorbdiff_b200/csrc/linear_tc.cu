@@ -44,17 +44,25 @@ namespace {
 
 using namespace adk::tc;
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 2, TC_UMMA_K = 16;
+constexpr int TC_BM = 128, TC_BK = 64, TC_UMMA_K = 16;
 constexpr int TC_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC_PROMOTE = 1;        // k-blocks accumulated in TMEM before promotion to registers
-constexpr int TC_EPI_COLS = TC_BN / 2;  // accumulator columns owned by one epilogue warp
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;                      // 16 KB
-constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;                      // 32 KB
-constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;    // 96 KB
 constexpr int TC_MAX_N = 2048;                                          // bias staged in shared memory
 constexpr uint32_t TC_XPOSE_BYTES = 32 * 64;                            // per epilogue warp: 32 rows x 16 fp32, swizzled
-constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_MAX_N * 4 + 8 * TC_XPOSE_BYTES;
-constexpr uint32_t TC_TMEM_COLS = 512;                                  // two 256-column accumulators
+// Two tile shapes.  Throughput: 128x256 tiles, 2 stages of 96 KB.  Latency (a handful of systems: M of a few
+// hundred rows would fill only N/256 of the 148 SMs): 128x32 tiles, 4 stages of 40 KB, 8x as many CTAs.
+template <int BN, int STAGES>
+struct TcShape {
+    static constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+    static constexpr uint32_t STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+    static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;                  // 4 TMEM lane quarters x column halves
+    static constexpr int EPI_COLS = BN / (EPI_WARPS / 4);               // accumulator columns owned by one epilogue warp
+    static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;    // two accumulator slots
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_MAX_N * 4 + 8 * TC_XPOSE_BYTES;
+};
+using TcWide = TcShape<256, 2>;
+using TcNarrow = TcShape<32, 4>;
 
 struct TcParams {
     int M, N, K;
@@ -78,18 +86,22 @@ __device__ __forceinline__ float ssilu_fast(float x) {
     return __fdividef(x, 1.0f + __expf(-x)) * (1.0f / 0.6f);
 }
 
-template <int ACT, bool OUT_F32, bool OUT_SPLIT>
+template <int TC_BN, int TC_STAGES, int ACT, bool OUT_F32, bool OUT_SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams P) {
+    using Shape = TcShape<TC_BN, TC_STAGES>;
+    constexpr uint32_t TC_B_BYTES = Shape::B_BYTES, TC_STAGE_BYTES = Shape::STAGE_BYTES, TC_TMEM_COLS = Shape::TMEM_COLS;
+    constexpr int TC_EPI_COLS = Shape::EPI_COLS, TC_EPI_WARPS = Shape::EPI_WARPS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;
-    // barriers (8 bytes each): full[2], empty[2], tmem_full[2], tmem_empty[2]; then the TMEM base address
+    // barriers (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base address
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 16u + 8u * s; };
-    auto tfull_bar = [&](int a) { return bar_base + 32u + 8u * a; };
-    auto tempty_bar = [&](int a) { return bar_base + 48u + 8u * a; };
-    const uint32_t tmem_slot = bar_base + 64u;
+    auto empty_bar = [&](int s) { return bar_base + 8u * TC_STAGES + 8u * s; };
+    auto tfull_bar = [&](int a) { return bar_base + 16u * TC_STAGES + 8u * a; };
+    auto tempty_bar = [&](int a) { return bar_base + 16u * TC_STAGES + 16u + 8u * a; };
+    const uint32_t tmem_slot = bar_base + 16u * TC_STAGES + 32u;
+    static_assert(16 * TC_STAGES + 36 <= 256, "barrier block");
     float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
     const uint32_t xpose_base = bar_base + 256u + TC_MAX_N * 4u;
     for (int i = threadIdx.x; i < P.N; i += TC_THREADS) s_bias[i] = P.bias ? P.bias[i] : 0.0f;
@@ -105,7 +117,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -186,8 +198,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
-    } else {
-        // ===================== epilogue (warps 2..5) =====================
+    } else if (warp - 2 < TC_EPI_WARPS) {
+        // ===================== epilogue (warps 2..9; 2..5 for the narrow tile) =====================
         const int q = warp & 3;               // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;     // which 128-column half of the accumulator it owns
         const int num_chunks = (num_k + TC_PROMOTE - 1) / TC_PROMOTE;
@@ -365,7 +377,11 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     alignas(64) CUtensorMap tmA, tmW;
     int rc;
     if ((rc = make_map_f16(&tmA, a_split, 2 * (uint64_t)a_plane_rows, (uint64_t)K, TC_BK, TC_BM)) != 0) return rc;
-    if ((rc = make_map_f16(&tmW, w_split, 2 * (uint64_t)N, (uint64_t)K, TC_BK, TC_BN)) != 0) return rc;
+    // few output tiles (a handful of systems): narrow tiles put 8x as many CTAs on the problem
+    const int tiles_wide = ((M + TC_BM - 1) / TC_BM) * ((N + 255) / 256);
+    const bool narrow = tiles_wide * 3 <= adk::tc::g_num_sms;
+    const int bn = narrow ? 32 : 256;
+    if ((rc = make_map_f16(&tmW, w_split, 2 * (uint64_t)N, (uint64_t)K, TC_BK, (uint32_t)bn)) != 0) return rc;
     TcParams P;
     P.M = M; P.N = N; P.K = K;
     P.a_lo_row = (int)a_plane_rows; P.w_lo_row = N;
@@ -375,11 +391,17 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     P.out_split_plane = out_plane_rows * (int64_t)N;
     P.out_split_scale = out_split_scale;
     P.status = status;
-    const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + TC_BN - 1) / TC_BN);
+    const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
     const int grid = tiles < adk::tc::g_num_sms ? tiles : adk::tc::g_num_sms;
     if (N > TC_MAX_N) return ADK_ERANGE;
     cudaStream_t st = adk::as_stream(stream);
-#define ADK_TC_LAUNCH(ACT_, F32_, SPL_) linear_tc_kernel<ACT_, F32_, SPL_><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmW, P)
+#define ADK_TC_LAUNCH(ACT_, F32_, SPL_)                                                                              \
+    do {                                                                                                            \
+        if (narrow)                                                                                                 \
+            linear_tc_kernel<32, 4, ACT_, F32_, SPL_><<<grid, TC_THREADS, TcNarrow::SMEM_BYTES, st>>>(tmA, tmW, P);  \
+        else                                                                                                        \
+            linear_tc_kernel<256, 2, ACT_, F32_, SPL_><<<grid, TC_THREADS, TcWide::SMEM_BYTES, st>>>(tmA, tmW, P);   \
+    } while (0)
     const bool f32 = out_f32 != nullptr, spl = out_split != nullptr;
     if (act == ADK_ACT_SSILU) {
         if (f32 && spl) ADK_TC_LAUNCH(ADK_ACT_SSILU, true, true);
@@ -411,10 +433,13 @@ int adk_linear_tc_set_attrs() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&adk::tc::g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e2 = cudaSuccess;
-#define ADK_TC_ATTR(ACT_, F32_, SPL_)                                                                          \
-    if (e2 == cudaSuccess)                                                                                     \
-        e2 = cudaFuncSetAttribute(linear_tc_kernel<ACT_, F32_, SPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  TC_SMEM_BYTES)
+#define ADK_TC_ATTR(ACT_, F32_, SPL_)                                                                                       \
+    if (e2 == cudaSuccess)                                                                                                  \
+        e2 = cudaFuncSetAttribute(linear_tc_kernel<256, 2, ACT_, F32_, SPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  TcWide::SMEM_BYTES);                                                                      \
+    if (e2 == cudaSuccess)                                                                                                  \
+        e2 = cudaFuncSetAttribute(linear_tc_kernel<32, 4, ACT_, F32_, SPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  TcNarrow::SMEM_BYTES)
     ADK_TC_ATTR(ADK_ACT_SSILU, true, true); ADK_TC_ATTR(ADK_ACT_SSILU, true, false); ADK_TC_ATTR(ADK_ACT_SSILU, false, true);
     ADK_TC_ATTR(ADK_ACT_NONE, true, true); ADK_TC_ATTR(ADK_ACT_NONE, true, false); ADK_TC_ATTR(ADK_ACT_NONE, false, true);
 #undef ADK_TC_ATTR
