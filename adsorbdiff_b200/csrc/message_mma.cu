@@ -485,6 +485,12 @@ extern "C" int adk_split_f16_transpose(const float* w, int rows, int cols, float
     return 0;
 }
 
+extern "C" int64_t adk_message_mma_smem_bytes(int R, int n_max) {
+    if (R < 16 || R > 128 || (R & 15) || n_max <= 0) return ADK_ERANGE;
+    const size_t b = mm_smem_bytes(R, n_max);
+    return b > 227 * 1024 ? (int64_t)ADK_ERANGE : (int64_t)b;
+}
+
 extern "C" int adk_message_mma(const int32_t* atom_off, int B, int n_max, const int32_t* row_start,
                                const int32_t* row_deg, const int32_t* e_src, const float* e_geo, const float* xh,
                                const float* vec_in, const void* wt_split, float w_scale, const float* b_rbf,

@@ -333,8 +333,9 @@ class PaiNN(nn.Module):
         p.sp_h = torch.zeros(2 * p.rows_n * F, **f16)         # hidden of the two-layer MLPs, K <= F
         p.sp_v = torch.zeros(2 * p.rows_3n * F, **f16)        # vec-wise inputs, K <= F
         p.wt_rbf = [torch.empty(2 * self.num_rbf * 3 * F, **f16) for _ in range(self.num_layers)]
-        # shared-memory footprint of the staged message kernel (see mm_smem_bytes in csrc/message_mma.cu)
-        p.mma_fits = 2 * self.num_rbf * 208 + 4 * self.num_rbf + 4 * p.n_max * 2 * 112 + 64 <= 227 * 1024
+        # does a system's staged slice fit the shared memory of the warp-MMA message kernel?  (else: adk_message)
+        p.mma_fits = (self.num_rbf % 16 == 0 and 16 <= self.num_rbf <= 128
+                      and _cabi.load().adk_message_mma_smem_bytes(self.num_rbf, p.n_max) > 0)
         self._plan_cache = p
         return p
 
@@ -483,7 +484,7 @@ class PaiNN(nn.Module):
             vin = p.vec[cur] if l > 0 else None  # vec == 0 before the first message
             vout = p.vec[1 - cur]
             vec_presplit = False
-            if self.msg == "mma" and R <= 128 and R % 16 == 0 and p.mma_fits:
+            if self.msg == "mma" and p.mma_fits:
                 wt = p.wt_rbf[l]
                 call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self.W_SCALE, ptr(wt),
                      ptr(p.status))

@@ -180,6 +180,10 @@ int adk_message_tc(const int32_t* atom_off, int B, const int32_t* sys_counts, co
  */
 int adk_split_f16_transpose(const float* w, int rows, int cols, float scale, void* dst, uint32_t* status,
                             void* stream);
+/* Dynamic shared memory adk_message_mma needs for systems of up to n_max atoms (weight planes + the staged
+ * source features of one system), or negative ADK_ERANGE if that exceeds the 227 KB of an sm_100a CTA (the
+ * caller then uses adk_message for the batch). */
+int64_t adk_message_mma_smem_bytes(int R, int n_max);
 int adk_message_mma(const int32_t* atom_off, int B, int n_max, const int32_t* row_start,
                     const int32_t* row_deg, const int32_t* e_src, const float* e_geo, const float* xh,
                     const float* vec_in, const void* wt_split, float w_scale, const float* b_rbf,

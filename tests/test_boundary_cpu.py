@@ -28,6 +28,8 @@ def test_neighbor_staging_capacity_query():
     assert lib.adk_neighbors_smem_bytes(90, 75, 50) > 0
     assert lib.adk_neighbors_smem_bytes(5000, 75, 50) < 0
     assert lib.adk_neighbors_smem_bytes(90, 5000, 50) < 0
+    assert 0 < lib.adk_message_mma_smem_bytes(128, 90) <= 227 * 1024
+    assert lib.adk_message_mma_smem_bytes(128, 400) < 0 and lib.adk_message_mma_smem_bytes(100, 90) < 0
 
 
 def test_state_dict_matches_reference_layout(weights):
