@@ -160,8 +160,8 @@ class Denoiser:
             if record:
                 self.frames = torch.empty(num_steps, plan.N, 3, dtype=torch.float32, device=dev)
 
-            def one_step():
-                net._run(plan, z, pos)
+            def one_step(weights_ready=False):
+                net._run(plan, z, pos, weights_ready=weights_ready)
                 call("adk_se3_step", dev, ptr(pos), ptr(plan.cell_f32), ptr(plan.atom_off), ptr(tags), ptr(fixed),
                      ptr(plan.out[0]), ptr(plan.out[1]), ptr(sched), ptr(step), B, ptr(max_upd))
 
@@ -180,8 +180,10 @@ class Denoiser:
                         net.check_status(plan)
                         graph = torch.cuda.CUDAGraph()
                         saved_pos, saved_step = pos.clone(), step.clone()
+                        # Between the EMA swap-in above and the swap-out below nobody else writes the parameters,
+                        # and the eager step just produced their fp16x2 planes: the replayed step does not redo it.
                         with torch.cuda.graph(graph):
-                            one_step()
+                            one_step(weights_ready=True)
                         # capture does not execute, but be explicit about state
                         pos.copy_(saved_pos)
                         step.copy_(saved_step)

@@ -464,11 +464,16 @@ class PaiNN(nn.Module):
         self._mlp2(p, p.cat, 2 * H, N, 2 * H, b1.update_net[0], b1.update_net[2], p.ho2, 2, presplit=tc)
         call("adk_head_gate", dev, ptr(p.ho2), ptr(p.v2p2), N, 1, None, ptr(out))
 
-    def _run(self, p: _Plan, z: torch.Tensor, pos: torch.Tensor, trace: Optional[dict] = None):
-        """Enqueue the whole forward on the current stream (capturable: no sync, no allocation)."""
+    def _run(self, p: _Plan, z: torch.Tensor, pos: torch.Tensor, trace: Optional[dict] = None,
+             weights_ready: bool = False):
+        """Enqueue the whole forward on the current stream (capturable: no sync, no allocation).
+        `weights_ready`: the fp16x2 operand planes of the weights (GEMM planes and the transposed rbf_proj planes
+        in this plan) were produced by an earlier `_run` and the parameters have not changed since -- only a
+        caller that owns the parameters for the duration may say so (the sampler, between its EMA swap-in and
+        swap-out); `forward` never does."""
         N, F, R = p.N, self.hidden_channels, self.num_rbf
         dev = p.device
-        if self.gemm == "tc" or self.msg == "tc":
+        if (self.gemm == "tc" or self.msg == "tc") and not weights_ready:
             self._resplit_weights(p)
         self._graph(p, pos)
         call("adk_embed", dev, ptr(z), ptr(self.atom_emb.embeddings.weight), self.atom_emb.embeddings.weight.shape[0],
@@ -486,8 +491,9 @@ class PaiNN(nn.Module):
             vec_presplit = False
             if self.msg == "mma" and p.mma_fits:
                 wt = p.wt_rbf[l]
-                call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self.W_SCALE, ptr(wt),
-                     ptr(p.status))
+                if not weights_ready:
+                    call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self.W_SCALE, ptr(wt),
+                         ptr(p.status))
                 call("adk_message_mma", dev, ptr(p.atom_off), p.B, p.n_max, ptr(p.row_start), ptr(p.row_deg),
                      ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wt),
                      self.W_SCALE, ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R,
