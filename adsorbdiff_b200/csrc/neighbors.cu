@@ -47,19 +47,20 @@ struct NbParams {
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 struct NbSmem {
-    size_t pos, off, neg, cand_d2, cand_id, kept, kept_cnt, rev_cnt, row_start, misc, total;
+    size_t pos, off, neg, img, cand_d2, cand_id, kept, kept_cnt, rev_cnt, row_start, misc, total;
     __host__ __device__ NbSmem(int n_max, int C, int k, int warps) {
         size_t o = 0;
         pos = o;       o = align16(o + sizeof(float) * 3 * n_max);
         off = o;       o = align16(o + sizeof(float) * 3 * C);
         neg = o;       o = align16(o + C);
+        img = o;       o = align16(o + sizeof(uint16_t) * C);
         cand_d2 = o;   o = align16(o + sizeof(uint32_t) * warps * CAND_MAX);
         cand_id = o;   o = align16(o + sizeof(uint32_t) * warps * CAND_MAX);
         kept = o;      o = align16(o + sizeof(uint32_t) * (size_t)n_max * k);
         kept_cnt = o;  o = align16(o + sizeof(int) * n_max);
         rev_cnt = o;   o = align16(o + sizeof(int) * n_max);
         row_start = o; o = align16(o + sizeof(int) * (n_max + 1));
-        misc = o;      o = align16(o + sizeof(int) * 4);
+        misc = o;      o = align16(o + sizeof(int) * 16);
         total = o;
     }
 };
@@ -74,6 +75,15 @@ __device__ __forceinline__ float4 edge_geometry(const float* s_pos, const float*
     float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
     if (fabsf(d) <= 1.0e-3f) d = 1.0e-3f;  // torch.isclose(d, 0, atol=1e-3)  (painn_denoising.py:366-367)
     return make_float4(d, vx / d, vy / d, vz / d);
+}
+
+// The distance alone (sort key of a CSR row): same arithmetic as edge_geometry, without the three divisions.
+__device__ __forceinline__ float edge_distance(const float* s_pos, const float* s_off, int C, int tgt, int src, int img) {
+    float vx = __fadd_rn(__fsub_rn(s_pos[3 * src + 0], s_pos[3 * tgt + 0]), s_off[img]);
+    float vy = __fadd_rn(__fsub_rn(s_pos[3 * src + 1], s_pos[3 * tgt + 1]), s_off[C + img]);
+    float vz = __fadd_rn(__fsub_rn(s_pos[3 * src + 2], s_pos[3 * tgt + 2]), s_off[2 * C + img]);
+    float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+    return fabsf(d) <= 1.0e-3f ? 1.0e-3f : d;
 }
 
 // Shrink a warp's candidate list to its k smallest by (d2 bits, position), keeping order.
@@ -144,13 +154,14 @@ __global__ void __launch_bounds__(NB_WARPS_MAX * 32) neighbors_kernel(NbParams P
     float* s_pos = reinterpret_cast<float*>(smem_raw + L.pos);
     float* s_off = reinterpret_cast<float*>(smem_raw + L.off);  // [3][C]
     unsigned char* s_neg = smem_raw + L.neg;
+    uint16_t* s_img = reinterpret_cast<uint16_t*>(smem_raw + L.img);  // images that can hold an in-cutoff pair, ascending
     uint32_t* s_cd2 = reinterpret_cast<uint32_t*>(smem_raw + L.cand_d2);
     uint32_t* s_cid = reinterpret_cast<uint32_t*>(smem_raw + L.cand_id);
     uint32_t* s_kept = reinterpret_cast<uint32_t*>(smem_raw + L.kept);
     int* s_kept_cnt = reinterpret_cast<int*>(smem_raw + L.kept_cnt);
     int* s_rev_cnt = reinterpret_cast<int*>(smem_raw + L.rev_cnt);
     int* s_row_start = reinterpret_cast<int*>(smem_raw + L.row_start);
-    int* s_misc = reinterpret_cast<int*>(smem_raw + L.misc);  // [0]=raw edge count
+    int* s_misc = reinterpret_cast<int*>(smem_raw + L.misc);  // [0]=raw edge count, [1]=viable images, [2..7]=bbox
 
     const int tid = threadIdx.x, lane = adk::lane_id(), warp = adk::warp_id();
 
@@ -173,32 +184,74 @@ __global__ void __launch_bounds__(NB_WARPS_MAX * 32) neighbors_kernel(NbParams P
     if (tid == 0) s_misc[0] = 0;
     __syncthreads();
 
+    // ---- phase 0b: image culling -------------------------------------------------------------
+    // An image whose shifted copy of the system's bounding box is farther than the cutoff from the box itself
+    // cannot contribute a pair (e.g. the two out-of-plane images of a slab with vacuum: 50 of 75).  The test is a
+    // lower bound on every pair distance with a 1e-3 A margin, so no in-cutoff candidate is ever dropped and the
+    // surviving images keep their index and order: results are bit-identical to the full enumeration.
+    if (warp == 0) {
+        float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        for (int j = lane; j < n; j += 32)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) { lo[x] = fminf(lo[x], s_pos[3 * j + x]); hi[x] = fmaxf(hi[x], s_pos[3 * j + x]); }
+#pragma unroll
+        for (int x = 0; x < 3; ++x)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[x] = fminf(lo[x], __shfl_xor_sync(ADK_FULL_MASK, lo[x], o));
+                hi[x] = fmaxf(hi[x], __shfl_xor_sync(ADK_FULL_MASK, hi[x], o));
+            }
+        const float reach = sqrtf(P.cutoff2) + 1.0e-3f;
+        int cv = 0;
+        for (int base = 0; base < C; base += 32) {
+            const int c = base + lane;
+            bool viable = false;
+            if (c < C) {
+                float g2 = 0.f;
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    const float o = s_off[x * C + c];
+                    const float gap = fmaxf(fmaxf((lo[x] + o) - hi[x], lo[x] - (hi[x] + o)), 0.f);
+                    g2 += gap * gap;
+                }
+                viable = g2 <= reach * reach;
+            }
+            const unsigned m = __ballot_sync(ADK_FULL_MASK, viable);
+            if (viable) s_img[cv + __popc(m & adk::lanemask_lt())] = (uint16_t)c;
+            cv += __popc(m);
+        }
+        if (lane == 0) s_misc[1] = cv;
+    }
+    __syncthreads();
+    const int Cv = s_misc[1];
+
     // ---- phase 1: candidates -> top-k -> kept half ----------------------------------------
     uint32_t* cd2 = s_cd2 + warp * CAND_MAX;
     uint32_t* cid = s_cid + warp * CAND_MAX;
-    const int total = n * C;
+    const int total = n * Cv;
     for (int i = warp; i < n; i += NB_WARPS) {
         const float pix = s_pos[3 * i], piy = s_pos[3 * i + 1], piz = s_pos[3 * i + 2];
         int cnt = 0;
-        if (C <= 96) {
-            // common case (75 images for an OC20 slab at 12 A): a lane keeps the offsets of its <= 3 images in
-            // registers and the warp walks the source atoms; enumeration order is still (j, image) ascending.
+        if (Cv <= 96) {
+            // common case (75 images for an OC20 slab at 12 A, 25 after culling): a lane keeps the offsets of its
+            // <= 3 images in registers and the warp walks the source atoms; enumeration order is still (j, image)
+            // ascending.
             float ox[3], oy[3], oz[3];
+            int ci[3];
 #pragma unroll
             for (int sl = 0; sl < 3; ++sl) {
-                const int cc = min(lane + 32 * sl, C - 1);
-                ox[sl] = s_off[cc]; oy[sl] = s_off[C + cc]; oz[sl] = s_off[2 * C + cc];
+                ci[sl] = s_img[min(lane + 32 * sl, max(Cv - 1, 0))];
+                ox[sl] = s_off[ci[sl]]; oy[sl] = s_off[C + ci[sl]]; oz[sl] = s_off[2 * C + ci[sl]];
             }
             for (int j = 0; j < n; ++j) {
                 const float pjx = s_pos[3 * j], pjy = s_pos[3 * j + 1], pjz = s_pos[3 * j + 2];
 #pragma unroll
                 for (int sl = 0; sl < 3; ++sl) {
-                    if (32 * sl < C) {  // warp-uniform
-                        const int c = lane + 32 * sl;
+                    if (32 * sl < Cv) {  // warp-uniform
                         const float p2x = __fadd_rn(pjx, ox[sl]), p2y = __fadd_rn(pjy, oy[sl]), p2z = __fadd_rn(pjz, oz[sl]);
                         const float dx = __fsub_rn(pix, p2x), dy = __fsub_rn(piy, p2y), dz = __fsub_rn(piz, p2z);
                         const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                        const bool ok = (c < C) && (d2 <= P.cutoff2) && (d2 > 0.0001f);
+                        const bool ok = (lane + 32 * sl < Cv) && (d2 <= P.cutoff2) && (d2 > 0.0001f);
                         const unsigned m = __ballot_sync(ADK_FULL_MASK, ok);
                         if (m) {
                             if (cnt + 32 > CAND_MAX) {
@@ -208,7 +261,7 @@ __global__ void __launch_bounds__(NB_WARPS_MAX * 32) neighbors_kernel(NbParams P
                             if (ok) {
                                 const int p = cnt + __popc(m & adk::lanemask_lt());
                                 cd2[p] = __float_as_uint(d2);
-                                cid[p] = ((uint32_t)j << 16) | (uint32_t)c;
+                                cid[p] = ((uint32_t)j << 16) | (uint32_t)ci[sl];
                             }
                             cnt += __popc(m);
                         }
@@ -216,15 +269,17 @@ __global__ void __launch_bounds__(NB_WARPS_MAX * 32) neighbors_kernel(NbParams P
                 }
             }
         } else {
-        int j = 0, c = lane;  // (j, c) of this lane's pair, advanced incrementally
-        while (c >= C) { c -= C; ++j; }
+        int j = 0, c = lane;  // (j, c) of this lane's pair (c indexes the surviving images), advanced incrementally
+        while (c >= Cv) { c -= Cv; ++j; }
         for (int base = 0; base < total; base += 32) {
             bool ok = false;
             float d2 = 0.f;
+            int img = 0;
             if (base + lane < total) {
-                float p2x = __fadd_rn(s_pos[3 * j], s_off[c]);
-                float p2y = __fadd_rn(s_pos[3 * j + 1], s_off[C + c]);
-                float p2z = __fadd_rn(s_pos[3 * j + 2], s_off[2 * C + c]);
+                img = s_img[c];
+                float p2x = __fadd_rn(s_pos[3 * j], s_off[img]);
+                float p2y = __fadd_rn(s_pos[3 * j + 1], s_off[C + img]);
+                float p2z = __fadd_rn(s_pos[3 * j + 2], s_off[2 * C + img]);
                 float dx = __fsub_rn(pix, p2x), dy = __fsub_rn(piy, p2y), dz = __fsub_rn(piz, p2z);
                 d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                 ok = (d2 <= P.cutoff2) && (d2 > 0.0001f);
@@ -238,12 +293,12 @@ __global__ void __launch_bounds__(NB_WARPS_MAX * 32) neighbors_kernel(NbParams P
                 if (ok) {
                     int p = cnt + __popc(m & adk::lanemask_lt());
                     cd2[p] = __float_as_uint(d2);
-                    cid[p] = ((uint32_t)j << 16) | (uint32_t)c;
+                    cid[p] = ((uint32_t)j << 16) | (uint32_t)img;
                 }
                 cnt += __popc(m);
             }
             c += 32;
-            while (c >= C) { c -= C; ++j; }
+            while (c >= Cv) { c -= Cv; ++j; }
         }
         }
         __syncwarp();
@@ -326,8 +381,8 @@ __global__ void __launch_bounds__(NB_WARPS_MAX * 32) neighbors_kernel(NbParams P
             if (e < s_kept_cnt[t]) {
                 uint32_t id = s_kept[(size_t)t * k + e];
                 int src = (int)(id >> 16), img = (int)(id & 0xffffu);
-                float4 g = edge_geometry(s_pos, s_off, C, t, src, img);
-                keys[m + e] = ((unsigned long long)__float_as_uint(g.x) << 32) | ((uint32_t)src << 16) | (uint32_t)img;
+                const float d = edge_distance(s_pos, s_off, C, t, src, img);
+                keys[m + e] = ((unsigned long long)__float_as_uint(d) << 32) | ((uint32_t)src << 16) | (uint32_t)img;
             }
         }
         m += s_kept_cnt[t];
@@ -345,9 +400,9 @@ __global__ void __launch_bounds__(NB_WARPS_MAX * 32) neighbors_kernel(NbParams P
                 unsigned hm = __ballot_sync(ADK_FULL_MASK, hit);
                 if (hit) {
                     int img = C - 1 - (int)(id & 0xffffu);
-                    float4 g = edge_geometry(s_pos, s_off, C, t, i, img);
+                    const float d = edge_distance(s_pos, s_off, C, t, i, img);
                     keys[m + __popc(hm & adk::lanemask_lt())] =
-                        ((unsigned long long)__float_as_uint(g.x) << 32) | ((uint32_t)i << 16) | (uint32_t)img;
+                        ((unsigned long long)__float_as_uint(d) << 32) | ((uint32_t)i << 16) | (uint32_t)img;
                 }
                 m += __popc(hm);
             }
