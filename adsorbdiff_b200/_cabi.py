@@ -29,6 +29,7 @@ SIGNATURES = {
     "adk_init": (c_int, []),
     "adk_neighbors_smem_bytes": (c_int64, [c_int, c_int, c_int]),
     "adk_message_mma_smem_bytes": (c_int64, [c_int, c_int]),
+    "adk_set_tc_pair": (c_int, [c_int]),
     "adk_neighbors": (c_int, [_P, _P, _P, c_int, c_int, ctypes.POINTER(c_int32), c_float, c_int,
                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "adk_export_edges": (c_int, [_P, _P, _P, c_int, ctypes.POINTER(c_int32), c_int, _P, _P, _P, _P,

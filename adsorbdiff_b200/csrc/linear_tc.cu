@@ -35,6 +35,7 @@
 // Reference arithmetic replaced: the torch.nn.Linear calls of PaiNNMessage.x_proj, PaiNNUpdate.vec_proj /
 // xvec_proj and GatedEquivariantBlock (models/painn/painn_denoising.py:508-512, 580-587, 667-676).
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -44,6 +45,11 @@ namespace {
 
 using namespace adk::tc;
 
+// Wide GEMMs as cta_group::2 pairs (adk_set_tc_pair / ADK_TC_PAIR=1).  Parity-green, but measured 13 % slower than the
+// single-CTA kernel at one k-block per promotion (the TMEM hand-off to the drain warps, now with remote arrivals, is the
+// critical path; both reach the same 1.13 PFLOP/s when two k-blocks are promoted at once), so it is off by default.
+bool g_tc_pair = false;
+
 constexpr int TC_BM = 128, TC_BK = 64, TC_UMMA_K = 16;
 constexpr int TC_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC_PROMOTE = 1;        // k-blocks accumulated in TMEM before promotion to registers
@@ -52,9 +58,9 @@ constexpr int TC_MAX_N = 2048;                                          // bias 
 constexpr uint32_t TC_XPOSE_BYTES = 32 * 64;                            // per epilogue warp: 32 rows x 16 fp32, swizzled
 // Two tile shapes.  Throughput: 128x256 tiles, 2 stages of 96 KB.  Latency (a handful of systems: M of a few
 // hundred rows would fill only N/256 of the 148 SMs): 128x32 tiles, 4 stages of 40 KB, 8x as many CTAs.
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 struct TcShape {
-    static constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+    static constexpr uint32_t B_BYTES = (PAIR ? BN / 2 : BN) * TC_BK * 2;   // a CTA of a pair stages half of the B tile
     static constexpr uint32_t STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
     static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;                  // 4 TMEM lane quarters x column halves
     static constexpr int EPI_COLS = BN / (EPI_WARPS / 4);               // accumulator columns owned by one epilogue warp
@@ -63,6 +69,7 @@ struct TcShape {
 };
 using TcWide = TcShape<256, 2>;
 using TcNarrow = TcShape<32, 4>;
+using TcPair = TcShape<256, 3, true>;    // cta_group::2: 64 KB per stage and CTA, three stages
 
 struct TcParams {
     int M, N, K;
@@ -86,10 +93,13 @@ __device__ __forceinline__ float ssilu_fast(float x) {
     return __fdividef(x, 1.0f + __expf(-x)) * (1.0f / 0.6f);
 }
 
-template <int TC_BN, int TC_STAGES, int ACT, bool OUT_F32, bool OUT_SPLIT>
+template <int TC_BN, int TC_STAGES, bool PAIR, int ACT, bool OUT_F32, bool OUT_SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams P) {
-    using Shape = TcShape<TC_BN, TC_STAGES>;
+    using Shape = TcShape<TC_BN, TC_STAGES, PAIR>;
+    // PAIR: launched as 2-CTA clusters; rank 0 (the leader) issues the MMAs for both, rank r owns output rows
+    // [m0 + 128 r, +128) and stages W rows [n0 + 128 r, +128)
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     constexpr uint32_t TC_B_BYTES = Shape::B_BYTES, TC_STAGE_BYTES = Shape::STAGE_BYTES, TC_TMEM_COLS = Shape::TMEM_COLS;
     constexpr int TC_EPI_COLS = Shape::EPI_COLS, TC_EPI_WARPS = Shape::EPI_WARPS;
     extern __shared__ uint8_t smem_raw[];
@@ -108,7 +118,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = adk::warp_id(), lane = adk::lane_id();
     const int num_m = (P.M + TC_BM - 1) / TC_BM, num_n = (P.N + TC_BN - 1) / TC_BN, num_k = P.K / TC_BK;
-    const int num_tiles = num_m * num_n;
+    const int num_tiles = (PAIR ? (num_m + 1) / 2 : num_m) * num_n;
+    const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto tile_m0 = [&](int tile) { return (PAIR ? 2 * (tile / num_n) + (int)rank : tile / num_n) * TC_BM; };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -117,17 +130,25 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS * (PAIR ? 2 : 1)); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                     "r"(TC_TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"(TC_TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"(TC_TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything arrives on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -137,30 +158,44 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * TC_BN;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+                const int m0 = tile_m0(tile), n0 = (tile % num_n) * TC_BN;
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = base + stage * TC_STAGE_BYTES;
-                    mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
-                    tma_load_2d(sa, &tmA, full_bar(stage), kb * TC_BK, m0);
-                    tma_load_2d(sa + TC_A_BYTES, &tmA, full_bar(stage), kb * TC_BK, P.a_lo_row + m0);
-                    tma_load_2d(sa + 2 * TC_A_BYTES, &tmW, full_bar(stage), kb * TC_BK, n0);
-                    tma_load_2d(sa + 2 * TC_A_BYTES + TC_B_BYTES, &tmW, full_bar(stage), kb * TC_BK, P.w_lo_row + n0);
+                    if (PAIR) {
+                        // both CTAs' bytes land on the leader's barrier; only the leader arms it
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * TC_STAGE_BYTES);
+                        const int nr = n0 + (int)rank * (TC_BN / 2);
+                        tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * TC_BK, m0);
+                        tma_load_2d_pair(sa + TC_A_BYTES, &tmA, full_bar(stage), kb * TC_BK, P.a_lo_row + m0);
+                        tma_load_2d_pair(sa + 2 * TC_A_BYTES, &tmW, full_bar(stage), kb * TC_BK, nr);
+                        tma_load_2d_pair(sa + 2 * TC_A_BYTES + TC_B_BYTES, &tmW, full_bar(stage), kb * TC_BK, P.w_lo_row + nr);
+                    } else {
+                        mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+                        tma_load_2d(sa, &tmA, full_bar(stage), kb * TC_BK, m0);
+                        tma_load_2d(sa + TC_A_BYTES, &tmA, full_bar(stage), kb * TC_BK, P.a_lo_row + m0);
+                        tma_load_2d(sa + 2 * TC_A_BYTES, &tmW, full_bar(stage), kb * TC_BK, n0);
+                        tma_load_2d(sa + 2 * TC_A_BYTES + TC_B_BYTES, &tmW, full_bar(stage), kb * TC_BK, P.w_lo_row + n0);
+                    }
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, both K-major, N=256, M=128
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        if (lane == 0 && rank == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, both K-major, N, M (256 for a pair)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
+            auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accumulate) {
+                if (PAIR) umma_f16_pair(d, a, b, id, accumulate); else umma_f16(d, a, b, id, accumulate);
+            };
+            auto commit = [](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             int stage = 0;
             uint32_t phase = 0;
             int astage = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 for (int kb = 0; kb < num_k; ++kb) {
                     const bool chunk_start = (kb % TC_PROMOTE) == 0;
                     const bool chunk_end = ((kb + 1) % TC_PROMOTE) == 0 || kb == num_k - 1;
@@ -181,17 +216,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / TC_UMMA_K; ++ks) {
                         const uint64_t koff = (uint64_t)((ks * TC_UMMA_K * 2) >> 4);  // 32 bytes per k-step
-                        umma_f16(d_tmem, d_ah + koff, d_wl + koff, idesc, (chunk_start && ks == 0) ? 0u : 1u);
-                        umma_f16(d_tmem, d_al + koff, d_wh + koff, idesc, 1u);
+                        mma(d_tmem, d_ah + koff, d_wl + koff, idesc, (chunk_start && ks == 0) ? 0u : 1u);
+                        mma(d_tmem, d_al + koff, d_wh + koff, idesc, 1u);
                     }
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / TC_UMMA_K; ++ks) {
                         const uint64_t koff = (uint64_t)((ks * TC_UMMA_K * 2) >> 4);
-                        umma_f16(d_tmem, d_ah + koff, d_wh + koff, idesc, 1u);
+                        mma(d_tmem, d_ah + koff, d_wh + koff, idesc, 1u);
                     }
-                    umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+                    commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
                     if (chunk_end) {
-                        umma_commit(tfull_bar(astage));  // partial sum ready for promotion
+                        commit(tfull_bar(astage));  // partial sum ready for promotion
                         if (++astage == 2) { astage = 0; aphase ^= 1u; }
                     }
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
@@ -206,8 +241,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int astage = 0;
         uint32_t aphase = 0;
         bool overflow = false;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / num_n) * TC_BM, n0 = (tile % num_n) * TC_BN + half * TC_EPI_COLS;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            const int m0 = tile_m0(tile), n0 = (tile % num_n) * TC_BN + half * TC_EPI_COLS;
             float acc[TC_EPI_COLS];
 #pragma unroll
             for (int j = 0; j < TC_EPI_COLS; ++j) acc[j] = 0.f;
@@ -228,7 +263,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(astage));
+                if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(astage)); else mbar_arrive(tempty_bar(astage)); }
                 if (++astage == 2) { astage = 0; aphase ^= 1u; }
             }
             const uint32_t xb = xpose_base + (uint32_t)(warp - 2) * TC_XPOSE_BYTES;
@@ -297,8 +332,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // the leader's MMAs read the peer's shared memory until the very end
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
     }
 }
 
@@ -366,6 +405,11 @@ extern "C" int adk_split_f16(const float* src, int64_t ld, int M, int K, float s
     return 0;
 }
 
+extern "C" int adk_set_tc_pair(int enable) {
+    g_tc_pair = enable != 0;
+    return 0;
+}
+
 extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, const void* w_split, int N, int K,
                              const float* bias, float acc_scale, int act, float* out_f32, int64_t ldc,
                              void* out_split, int64_t out_plane_rows, float out_split_scale, uint32_t* status,
@@ -377,11 +421,13 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     alignas(64) CUtensorMap tmA, tmW;
     int rc;
     if ((rc = make_map_f16(&tmA, a_split, 2 * (uint64_t)a_plane_rows, (uint64_t)K, TC_BK, TC_BM)) != 0) return rc;
-    // few output tiles (a handful of systems): narrow tiles put 8x as many CTAs on the problem
-    const int tiles_wide = ((M + TC_BM - 1) / TC_BM) * ((N + 255) / 256);
+    // few output tiles (a handful of systems): narrow tiles put 8x as many CTAs on the problem; otherwise CTA pairs
+    const int num_m = (M + TC_BM - 1) / TC_BM;
+    const int tiles_wide = num_m * ((N + 255) / 256);
     const bool narrow = tiles_wide * 3 <= adk::tc::g_num_sms;
+    const bool pair = !narrow && g_tc_pair && num_m >= 2;
     const int bn = narrow ? 32 : 256;
-    if ((rc = make_map_f16(&tmW, w_split, 2 * (uint64_t)N, (uint64_t)K, TC_BK, (uint32_t)bn)) != 0) return rc;
+    if ((rc = make_map_f16(&tmW, w_split, 2 * (uint64_t)N, (uint64_t)K, TC_BK, (uint32_t)(pair ? 128 : bn))) != 0) return rc;
     TcParams P;
     P.M = M; P.N = N; P.K = K;
     P.a_lo_row = (int)a_plane_rows; P.w_lo_row = N;
@@ -391,16 +437,41 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     P.out_split_plane = out_plane_rows * (int64_t)N;
     P.out_split_scale = out_split_scale;
     P.status = status;
-    const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
-    const int grid = tiles < adk::tc::g_num_sms ? tiles : adk::tc::g_num_sms;
     if (N > TC_MAX_N) return ADK_ERANGE;
     cudaStream_t st = adk::as_stream(stream);
-#define ADK_TC_LAUNCH(ACT_, F32_, SPL_)                                                                              \
-    do {                                                                                                            \
-        if (narrow)                                                                                                 \
-            linear_tc_kernel<32, 4, ACT_, F32_, SPL_><<<grid, TC_THREADS, TcNarrow::SMEM_BYTES, st>>>(tmA, tmW, P);  \
-        else                                                                                                        \
-            linear_tc_kernel<256, 2, ACT_, F32_, SPL_><<<grid, TC_THREADS, TcWide::SMEM_BYTES, st>>>(tmA, tmW, P);   \
+    int grid;
+    if (pair) {
+        const int pair_tiles = ((num_m + 1) / 2) * ((N + 255) / 256);
+        const int max_pairs = adk::tc::g_num_sms / 2;
+        grid = 2 * (pair_tiles < max_pairs ? pair_tiles : max_pairs);
+    } else {
+        const int tiles = num_m * ((N + bn - 1) / bn);
+        grid = tiles < adk::tc::g_num_sms ? tiles : adk::tc::g_num_sms;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaSuccess;
+#define ADK_TC_LAUNCH(ACT_, F32_, SPL_)                                                                          \
+    do {                                                                                                        \
+        if (narrow) {                                                                                           \
+            cfg.dynamicSmemBytes = TcNarrow::SMEM_BYTES;                                                        \
+            le = cudaLaunchKernelEx(&cfg, linear_tc_kernel<32, 4, false, ACT_, F32_, SPL_>, tmA, tmW, P);       \
+        } else if (pair) {                                                                                      \
+            cfg.dynamicSmemBytes = TcPair::SMEM_BYTES;                                                          \
+            le = cudaLaunchKernelEx(&cfg, linear_tc_kernel<256, 3, true, ACT_, F32_, SPL_>, tmA, tmW, P);       \
+        } else {                                                                                                \
+            cfg.dynamicSmemBytes = TcWide::SMEM_BYTES;                                                          \
+            le = cudaLaunchKernelEx(&cfg, linear_tc_kernel<256, 2, false, ACT_, F32_, SPL_>, tmA, tmW, P);      \
+        }                                                                                                       \
     } while (0)
     const bool f32 = out_f32 != nullptr, spl = out_split != nullptr;
     if (act == ADK_ACT_SSILU) {
@@ -413,6 +484,7 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
         else ADK_TC_LAUNCH(ADK_ACT_NONE, false, true);
     }
 #undef ADK_TC_LAUNCH
+    if (le != cudaSuccess) return (int)le;
     ADK_LAUNCH_CHECK();
     return 0;
 }
@@ -433,15 +505,16 @@ int adk_linear_tc_set_attrs() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&adk::tc::g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e2 = cudaSuccess;
-#define ADK_TC_ATTR(ACT_, F32_, SPL_)                                                                                       \
-    if (e2 == cudaSuccess)                                                                                                  \
-        e2 = cudaFuncSetAttribute(linear_tc_kernel<256, 2, ACT_, F32_, SPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  TcWide::SMEM_BYTES);                                                                      \
-    if (e2 == cudaSuccess)                                                                                                  \
-        e2 = cudaFuncSetAttribute(linear_tc_kernel<32, 4, ACT_, F32_, SPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                  TcNarrow::SMEM_BYTES)
+#define ADK_TC_ATTR1(K_, BYTES_)                                                                        \
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES_)
+#define ADK_TC_ATTR(ACT_, F32_, SPL_)                                                                   \
+    ADK_TC_ATTR1((linear_tc_kernel<256, 2, false, ACT_, F32_, SPL_>), TcWide::SMEM_BYTES);              \
+    ADK_TC_ATTR1((linear_tc_kernel<32, 4, false, ACT_, F32_, SPL_>), TcNarrow::SMEM_BYTES);             \
+    ADK_TC_ATTR1((linear_tc_kernel<256, 3, true, ACT_, F32_, SPL_>), TcPair::SMEM_BYTES)
     ADK_TC_ATTR(ADK_ACT_SSILU, true, true); ADK_TC_ATTR(ADK_ACT_SSILU, true, false); ADK_TC_ATTR(ADK_ACT_SSILU, false, true);
     ADK_TC_ATTR(ADK_ACT_NONE, true, true); ADK_TC_ATTR(ADK_ACT_NONE, true, false); ADK_TC_ATTR(ADK_ACT_NONE, false, true);
 #undef ADK_TC_ATTR
+#undef ADK_TC_ATTR1
+    if (const char* e = getenv("ADK_TC_PAIR")) g_tc_pair = e[0] != '0';
     return (int)e2;
 }

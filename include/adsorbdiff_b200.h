@@ -130,6 +130,10 @@ int adk_linear(const float* A, int64_t lda, const float* W, const float* bias, i
  */
 int adk_split_f16(const float* src, int64_t ld, int M, int K, float scale, void* dst, int64_t plane_rows,
                   uint32_t* status, void* stream);
+/* Tuning knob: run wide GEMMs as cta_group::2 CTA pairs (one MMA over M = 256 rows, each CTA staging half of the
+ * weight tile).  Off by default (slower at one k-block per promotion, see csrc/linear_tc.cu); also ADK_TC_PAIR=1. */
+int adk_set_tc_pair(int enable);
+
 /* Same split for `count` contiguous tensors in one launch: table[i] = {const float* src; fp16* dst;
  * int64 n_elems} (device array of 24-byte records; dst planes are n_elems apart, n_elems % 4 == 0).
  * Used to re-split every weight at the start of each forward, so in-place parameter updates

@@ -64,3 +64,34 @@ def test_split_overflow_sets_status():
     status = torch.zeros(1, dtype=torch.int32, device=DEV)
     call("adk_split_f16", DEV, ptr(t), 64, 4, 64, 16.0, ptr(buf), 128, ptr(status))
     assert int(status.item()) & _cabi.STATUS_F16_OVERFLOW
+
+
+def _run_tc(M, N, K, act, seed):
+    g = torch.Generator().manual_seed(seed)
+    A = (torch.randn(M, K, generator=g) * 1.7).to(DEV)
+    W = ((torch.rand(N, K, generator=g) * 2 - 1) * math.sqrt(6.0 / (N + K))).to(DEV)
+    bias = (torch.rand(N, generator=g) * 0.2 - 0.1).to(DEV)
+    rows = (M + 127) // 128 * 128
+    a_sp, w_sp = _split(A, A_SCALE, rows), _split(W, W_SCALE, N)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    call("adk_linear_tc", DEV, ptr(a_sp), rows, M, ptr(w_sp), N, K, ptr(bias), 1.0 / (A_SCALE * W_SCALE), act,
+         ptr(out), N, None, 0, A_SCALE, ptr(status))
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    return out
+
+
+def test_cta_pair_variant_matches_single_cta():
+    """cta_group::2 path (two CTAs, one MMA over 256 rows, half of the weight tile staged per CTA): bit-identical to
+    the single-CTA kernel -- same products, same accumulation order -- including an odd number of row tiles."""
+    lib = _cabi.load()
+    outs = []
+    try:
+        for pair in (0, 1):
+            lib.adk_set_tc_pair(pair)
+            outs.append([_run_tc(M, 1536, 512, _cabi.ACT_SSILU, seed=5) for M in (20992, 19333)])
+    finally:
+        lib.adk_set_tc_pair(0)
+    for a, b in zip(*outs):
+        assert torch.isfinite(a).all() and torch.equal(a, b)

@@ -76,9 +76,12 @@ def test_forward_matches_oracle_and_reference(name, gemm, msg, model, golden, we
     """Per-layer node features and both outputs, for both GEMM engines (tcgen05 fp16x2-split and
     exact-fp32 SIMT) and both message kernels (rbf_proj on tcgen05 / 16-tap SIMT).  Stated tolerance (all relative to the tensor's max magnitude):
       * vs the fp64 evaluation of the oracle (ground truth): 1e-5 -- the north-star bar;
-      * vs the fp32 oracle / the unmodified reference's frozen fp32 output: 2e-5, because the
+      * vs the unmodified reference's frozen fp32 output (tests/golden, a fixed file): 2e-5, because the
         reference's own fp32 result sits 3-5e-6 from ground truth on these networks (printed)
-        and the two fp32 evaluations err independently (different summation order)."""
+        and the two fp32 evaluations err independently (different summation order);
+      * vs the fp32 oracle evaluated here on the host CPU: sanity bound 1e-4 only -- that evaluation is
+        not reproducible across hosts (torch's CPU GEMM / reduction order depends on core count and ISA;
+        one B200 box measured 2.4e-5 where the others measure 4e-6 for the very same CUDA output)."""
     _reset_sticky_pbc()
     make, pbc = CASES[name]
     b, g = make(), golden(name)
@@ -99,14 +102,14 @@ def test_forward_matches_oracle_and_reference(name, gemm, msg, model, golden, we
         e64, e32 = rel(tr_c[key], tr64[key]), rel(tr_c[key], tr32[key])
         worst = max(worst, e64)
         assert e64 < FEATURE_TOL, (key, e64)
-        assert e32 < 2 * FEATURE_TOL, (key, e32)
+        assert e32 < 10 * FEATURE_TOL, (key, e32)
     for got, r32, r64, gk in zip(outs, o32, o64, ("forces", "forces2")):
         e64, e32, eref = rel(got, r64), rel(got, r32), rel(r32, r64)
         egold = rel(got, torch.from_numpy(g[gk]))
         print(f"{name}/{gemm}+{msg}/{gk}: cuda-vs-fp64 {e64:.2e}  reference(fp32)-vs-fp64 {eref:.2e}  cuda-vs-reference {egold:.2e}"
               f"  (worst feature vs fp64 {worst:.2e})")
         assert e64 < FEATURE_TOL, (gk, e64)
-        assert e32 < 2 * FEATURE_TOL and egold < 2 * FEATURE_TOL, (gk, e32, egold)
+        assert egold < 2 * FEATURE_TOL and e32 < 10 * FEATURE_TOL, (gk, e32, egold)
 
 
 def test_float_attribute_inputs(model, weights):
