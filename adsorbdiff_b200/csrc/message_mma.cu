@@ -523,9 +523,10 @@ extern "C" int adk_message_mma(const int32_t* atom_off, int B, int n_max, const 
     P.x_io = x_io; P.vec_out = vec_out;
     P.vsplit = reinterpret_cast<__half*>(vec_split); P.vsplit_plane = split_rows * (int64_t)F;
     P.vsplit_scale = split_scale; P.status = status;
-    // one CTA per (system, feature slice) fills the GPU from ~10 systems on; below that split the rows as well
+    // one CTA per (system, feature slice) fills the GPU from ~10 systems on; below that split the rows as well,
+    // as long as all CTAs are resident at once (one per SM)
     int row_splits = 1;
-    while (row_splits < 4 && (long long)B * (F / MM_SF) * row_splits * 2 <= 160) row_splits *= 2;
+    while (row_splits < 8 && (long long)B * (F / MM_SF) * row_splits * 2 <= 148) row_splits *= 2;
     message_mma_kernel<<<dim3(B, F / MM_SF, row_splits), MM_THREADS, smem, adk::as_stream(stream)>>>(P);
     ADK_LAUNCH_CHECK();
     return 0;
