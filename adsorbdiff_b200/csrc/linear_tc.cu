@@ -7,14 +7,15 @@
 // k-step.  Measured error vs fp64 is ~1e-7 of the output scale -- below a plain fp32 SGEMM's --
 // at 3 of the 2.25 PFLOP/s fp16 MMAs per product instead of 3 of the 1.1 PFLOP/s TF32 ones.
 //
-// Structure (one CTA per SM, persistent over 128x256 output tiles):
+// Structure (one CTA per SM, 384 threads, persistent over 128x256 output tiles; warps 2-3 idle so that the
+// producer warps form a warpgroup of their own for setmaxnreg):
 //   warp 0    TMA producer : cp.async.bulk.tensor 2-D loads of the four operand tiles of a k-block
 //                            (A hi/lo 128x64, W hi/lo 256x64 fp16, 128-byte swizzle) into a
 //                            2-stage shared-memory ring, mbarrier complete_tx
 //   warp 1    MMA issuer   : one thread issues 12 tcgen05.mma per k-block (4 k-steps x {hh, hl, lh})
 //                            into one of two 256-column TMEM accumulators; tcgen05.commit frees the
 //                            smem stage / publishes the accumulator
-//   warps 2-9 epilogue     : the tensor core's fp32 accumulate truncates (measured: error grows
+//   warps 4-11 epilogue    : the tensor core's fp32 accumulate truncates (measured: error grows
 //                            linearly with the number of accumulate steps, 5e-7 at K=64 -> 4.8e-6 at
 //                            K=1024 of the output scale), so the TMEM accumulator only ever holds a
 //                            PARTIAL sum over TC_PROMOTE k-blocks (K=64, 12 MMA steps); these warps
@@ -51,7 +52,8 @@ using namespace adk::tc;
 bool g_tc_pair = false;
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_UMMA_K = 16;
-constexpr int TC_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TC_THREADS = 384;      // warpgroup 0: TMA warp, MMA warp, two idle; warpgroups 1-2: 8 epilogue warps
+constexpr int TC_EPI_WARP0 = 4;      // first epilogue warp
 constexpr int TC_PROMOTE = 1;        // k-blocks accumulated in TMEM before promotion to registers
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;                      // 16 KB
 constexpr int TC_MAX_N = 2048;                                          // bias staged in shared memory
@@ -152,9 +154,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // The producer warpgroup needs a handful of registers; the epilogue warps want 128 accumulators plus two
+    // TMEM loads in flight.  384 x 168 = 128 x 40 + 256 x 232.
+    // (each role branch below starts with its own setmaxnreg so that ptxas sees the limit on that path)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -184,6 +190,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (lane == 0 && rank == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, both K-major, N, M (256 for a pair)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
@@ -233,10 +240,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
-    } else if (warp - 2 < TC_EPI_WARPS) {
-        // ===================== epilogue (warps 2..9; 2..5 for the narrow tile) =====================
+    } else if (warp < TC_EPI_WARP0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // idle warps of the producer warpgroup
+    } else if (warp - TC_EPI_WARP0 >= TC_EPI_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");  // idle warps of an epilogue warpgroup (narrow tile)
+    } else {
+        // ===================== epilogue (warps 4..11; 4..7 for the narrow tile) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int q = warp & 3;               // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;     // which 128-column half of the accumulator it owns
+        const int half = (warp - TC_EPI_WARP0) >> 2;     // which column half of the accumulator it owns
         const int num_chunks = (num_k + TC_PROMOTE - 1) / TC_PROMOTE;
         int astage = 0;
         uint32_t aphase = 0;
@@ -252,21 +264,34 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)astage * TC_BN +
                                        (uint32_t)half * TC_EPI_COLS;
+                // RZ compensation (see header comment): 3 partial sums out of 4 are scaled by 1 + 2^-23
+                const float gain = ((ch & 3) != 3) ? 1.00000011920928955078125f : 1.0f;
+                if (TC_EPI_COLS >= 64) {
+                    // two loads in flight per wait: the ~230-cycle round trip of a tcgen05.ld is paid twice per
+                    // drain instead of four times (the drain is the pace-setter of this kernel)
 #pragma unroll
-                for (int c = 0; c < TC_EPI_COLS / 32; ++c) {
+                    for (int c = 0; c < TC_EPI_COLS / 64; ++c) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32_async(t_row + c * 64, v0);
+                        tmem_ld32_async(t_row + c * 64 + 32, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c * 64 + j] = fmaf(__uint_as_float(v0[j]), gain, acc[c * 64 + j]);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c * 64 + 32 + j] = fmaf(__uint_as_float(v1[j]), gain, acc[c * 64 + 32 + j]);
+                    }
+                } else {
                     uint32_t v[32];
-                    tmem_ld32(t_row + c * 32, v);
-                    // RZ compensation (see header comment): 3 partial sums out of 4 are scaled by 1 + 2^-23
-                    const float gain = ((ch & 3) != 3) ? 1.00000011920928955078125f : 1.0f;
+                    tmem_ld32(t_row, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fmaf(__uint_as_float(v[j]), gain, acc[c * 32 + j]);
+                    for (int j = 0; j < 32; ++j) acc[j] = fmaf(__uint_as_float(v[j]), gain, acc[j]);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(astage)); else mbar_arrive(tempty_bar(astage)); }
                 if (++astage == 2) { astage = 0; aphase ^= 1u; }
             }
-            const uint32_t xb = xpose_base + (uint32_t)(warp - 2) * TC_XPOSE_BYTES;
+            const uint32_t xb = xpose_base + (uint32_t)(warp - TC_EPI_WARP0) * TC_XPOSE_BYTES;
 #pragma unroll
             for (int pc = 0; pc < TC_EPI_COLS / 16; ++pc) {
                 const int n = n0 + pc * 16;
