@@ -332,6 +332,7 @@ class PaiNN(nn.Module):
         p.sp_x = torch.zeros(2 * p.rows_n * 2 * F, **f16)     # node-wise inputs, K <= 2F
         p.sp_h = torch.zeros(2 * p.rows_n * F, **f16)         # hidden of the two-layer MLPs, K <= F
         p.sp_v = torch.zeros(2 * p.rows_3n * F, **f16)        # vec-wise inputs, K <= F
+        p.sp_hv = torch.zeros(2 * p.rows_3n * (F // 2), **f16)  # the heads' hidden vec channel, K = F/2
         p.wt_rbf = [torch.empty(2 * self.num_rbf * 3 * F, **f16) for _ in range(self.num_layers)]
         # does a system's staged slice fit the shared memory of the warp-MMA message kernel?  (else: adk_message)
         p.mma_fits = (self.num_rbf % 16 == 0 and 16 <= self.num_rbf <= 128
@@ -432,15 +433,16 @@ class PaiNN(nn.Module):
             self._linear(p, A, lda, lin0, M, _cabi.ACT_SSILU, p.h1, lin0.weight.shape[0])
             self._linear(p, p.h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
 
-    def _vec_linear(self, p, vec, K, lins_outs, presplit=False):
+    def _vec_linear(self, p, vec, K, lins_outs, presplit=False, planes=None):
         """vec-wise bias-free projections of [3N, K] (vec_proj, vec1_proj, vec2_proj); one split feeds all."""
         M = 3 * p.N
+        planes = p.sp_v if planes is None else planes
         if not presplit and any(self._tc_ok(lin) for lin, _ in lins_outs):
-            self._split(p, vec, K, M, K, p.sp_v, p.rows_3n, self.V_SCALE)
+            self._split(p, vec, K, M, K, planes, p.rows_3n, self.V_SCALE)
         for lin, out in lins_outs:
             n_out = lin.weight.shape[0]
             if self._tc_ok(lin):
-                self._linear_tc(p, p.sp_v, p.rows_3n, M, lin, _cabi.ACT_NONE, out_f32=out, ldc=n_out, a_scale=self.V_SCALE)
+                self._linear_tc(p, planes, p.rows_3n, M, lin, _cabi.ACT_NONE, out_f32=out, ldc=n_out, a_scale=self.V_SCALE)
             else:
                 self._linear(p, vec, K, lin, M, _cabi.ACT_NONE, out, n_out)
 
@@ -457,7 +459,7 @@ class PaiNN(nn.Module):
         self._mlp2(p, p.cat, 2 * F, N, 2 * F, b0.update_net[0], b0.update_net[2], p.xn, F, presplit=tc)  # (s|g)
         call("adk_head_gate", dev, ptr(p.xn), ptr(p.v2p), N, H, ptr(p.hx), ptr(p.hv))
         # block 1: H -> 1
-        self._vec_linear(p, p.hv, H, [(b1.vec1_proj, p.v1p), (b1.vec2_proj, p.v2p2)])
+        self._vec_linear(p, p.hv, H, [(b1.vec1_proj, p.v1p), (b1.vec2_proj, p.v2p2)], planes=p.sp_hv)
         tc = self._tc_ok(b1.update_net[0])
         call("adk_head_prep", dev, ptr(p.hx), ptr(p.v1p), N, H, None if tc else ptr(p.cat), ptr(p.sp_x) if tc else None,
              p.rows_n, self.A_SCALE, ptr(p.status))
@@ -530,9 +532,10 @@ class PaiNN(nn.Module):
         try:
             self._head(p, self.out_forces, p.x, vec, p.out[0], presplit=False)
             if self.so3_denoising:
-                if self.gemm == "tc":  # the first head's block 1 reused the vec planes: split again
-                    self._split(p, vec, F, 3 * N, F, p.sp_v, p.rows_3n, self.V_SCALE)
-                self._head(p, self.out_forces2, p.x, vec, p.out[1], presplit=True)
+                # the first head split `vec` into p.sp_v (its hidden channel has planes of its own): reuse them
+                b0 = self.out_forces.output_network[0]
+                self._head(p, self.out_forces2, p.x, vec, p.out[1],
+                           presplit=any(self._tc_ok(l) for l in (b0.vec1_proj, b0.vec2_proj)))
         finally:
             self.gemm = saved_gemm
 

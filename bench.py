@@ -368,6 +368,12 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": msg_bytes_per_launch,
                     "peak_source": peaks["source"],
                     "note": "compute/shared-memory bound by design (per-edge tensors never reach HBM); see DESIGN.md 4"}
+        # the same kernel against the tensor roofline: algorithmic rbf_proj FLOPs (2*R*3F per edge)
+        rbf_flops = 2.0 * model.num_rbf * 3 * F * E
+        roofline["tensor_view"] = {"algorithmic_tflops": round(rbf_flops / (per * 1e-3) / 1e12, 1), "peak": tensor_peak,
+                                   "frac": round(rbf_flops / (per * 1e-3) / 1e12 / tensor_peak, 4),
+                                   "note": "dense-equivalent rbf_proj FLOPs; the kernel evaluates only the ~35-centre band "
+                                           "as fp16x2-split mma.sync (3 passes) next to the SIMT message math"}
     roofline["tensor_kernel"] = {"name": "linear_tc_kernel", "ms_per_step": round(tc_ms, 3),
                                  "mma_tflops_fp16": round(3.0 * tc_flops / max(tc_ms, 1e-9) / 1e9, 1),
                                  "frac_of_peak": round(3.0 * tc_flops / max(tc_ms, 1e-9) / 1e9 / tensor_peak, 4)}
