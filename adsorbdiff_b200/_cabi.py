@@ -42,7 +42,7 @@ SIGNATURES = {
     "adk_linear_tc": (c_int, [_P, c_int64, c_int, _P, c_int, c_int, _P, c_float, c_int, _P, c_int64,
                               _P, c_int64, c_float, _P, _P]),
     "adk_message": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int,
-                            _P, _P, _P, c_int, c_int, _P]),
+                            _P, _P, _P]),
     "adk_message_tc": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_int, c_int, c_int,
                                c_float, c_int, c_float, _P, _P, _P]),
     "adk_split_f16_transpose": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P]),

@@ -46,8 +46,6 @@ struct MsParams {
     int env_p;
     float* x_io;
     float* vec_out;
-    const int32_t* atom_off;  // system segmentation (staged variant)
-    int n_max;
 };
 
 __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
@@ -217,163 +215,12 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Staged variant: CTA = (one system) x (slice of SF features).  Every source atom of a system
-// appears in ~50 in-edge rows, so gathering xh[j] / vec[j] per edge from L2 (12 KB per edge)
-// made the row-tiled kernel above L2-bound.  Here the system's xh and vec slices are staged in
-// shared memory once (n x 6 x SF floats) next to the w_rbf slice and all per-edge gathers are
-// shared-memory reads: HBM/L2 traffic drops to the algorithmic minimum (each feature read once).
-// One lane owns one feature; otherwise the same 4-edge union-window scheme.
-// ------------------------------------------------------------------------------------------
-constexpr int SY_THREADS = 512;
-constexpr int SY_WARPS = SY_THREADS / 32;
-constexpr int SF = 32;
-
-__host__ __device__ inline size_t sys_smem_bytes(int R, int n_max) {
-    return sizeof(float) * ((size_t)R * 3 * SF + ((R + 3) & ~3) + (size_t)n_max * 6 * SF) +
-           sizeof(float4) * 32 * SY_WARPS;
-}
-
-__global__ void __launch_bounds__(SY_THREADS, 1) message_sys_kernel(MsParams P) {
-    extern __shared__ __align__(16) float s_w[];  // [R][3][SF]
-    const int F = P.F, R = P.R;
-    float* s_mu = s_w + (size_t)R * 3 * SF;                                   // [R]
-    float4* s_g_all = reinterpret_cast<float4*>(s_mu + ((R + 3) & ~3));       // [SY_WARPS][32]
-    float* s_xh = reinterpret_cast<float*>(s_g_all + 32 * SY_WARPS);         // [n][3][SF]
-    float* s_vec = s_xh + (size_t)P.n_max * 3 * SF;                           // [n][3][SF]
-    const int b = blockIdx.x;
-    const int f0 = blockIdx.y * SF;
-    const int a0 = P.atom_off[b], n = P.atom_off[b + 1] - a0;
-    const int lane = adk::lane_id(), warp = adk::warp_id();
-    const bool has_vec = P.vec_in != nullptr;
-
-    // stage: weight slice (lane <-> feature row of w_rbf, conflict-free stores) ...
-    for (int r = threadIdx.x; r < 3 * SF; r += SY_THREADS) {
-        const int g = r / SF, f = r - g * SF;
-        const float4* src = reinterpret_cast<const float4*>(P.w_rbf + (size_t)(g * F + f0 + f) * R);
-        for (int kq = 0; kq < R / 4; ++kq) {
-            float4 w = src[kq];
-            s_w[((kq * 4 + 0) * 3 + g) * SF + f] = w.x;
-            s_w[((kq * 4 + 1) * 3 + g) * SF + f] = w.y;
-            s_w[((kq * 4 + 2) * 3 + g) * SF + f] = w.z;
-            s_w[((kq * 4 + 3) * 3 + g) * SF + f] = w.w;
-        }
-    }
-    for (int k = threadIdx.x; k < R; k += SY_THREADS) s_mu[k] = P.rbf_offset[k];
-    // ... and the system's source features: one 128-byte segment per (atom, group) per warp
-    for (int seg = warp; seg < n * 3; seg += SY_WARPS) {
-        const int j = seg / 3, g = seg - j * 3;
-        s_xh[seg * SF + lane] = P.xh[(size_t)(a0 + j) * 3 * F + g * F + f0 + lane];
-        if (has_vec) s_vec[seg * SF + lane] = P.vec_in[(size_t)(a0 + j) * 3 * F + g * F + f0 + lane];
-    }
-    __syncthreads();
-
-    float4* s_g = s_g_all + warp * 32;
-    float bias[3];
-#pragma unroll
-    for (int g = 0; g < 3; ++g) bias[g] = P.b_rbf[g * F + f0 + lane];
-    const float inv_sqrt_3 = 0.57735026918962576451f;
-    const float inv_sqrt_h = 1.0f / sqrtf((float)F);
-
-    for (int tl = warp; tl < n; tl += SY_WARPS) {
-        const int t = a0 + tl;
-        const int start = P.row_start[t], deg = P.row_deg[t];
-        float dx = 0.f, dv[3] = {0.f, 0.f, 0.f};
-        int e0 = 0;
-        while (e0 < deg) {
-            int my_src = 0, my_klo = 0;
-            float4 my_geo = make_float4(0.f, 0.f, 0.f, 0.f);
-            float my_s = 0.f, my_env = 0.f;
-            if (lane < EG && e0 + lane < deg) {
-                my_src = P.e_src[start + e0 + lane] - a0;
-                my_geo = P.e_geo[start + e0 + lane];
-                my_s = my_geo.x * P.inv_cutoff;
-                float sp = my_s;
-                for (int q = 1; q < P.env_p; ++q) sp *= my_s;
-                float env = 1.0f + P.env_a * sp;
-                sp *= my_s; env += P.env_b * sp;
-                sp *= my_s; env += P.env_c * sp;
-                my_env = (my_s < 1.0f) ? env : 0.0f;
-                my_klo = (int)floorf(my_s * (float)(R - 1)) - (NTAPS / 2 - 1);
-                my_klo = max(0, min(my_klo, R - NTAPS));
-            }
-            const int klo0 = __shfl_sync(ADK_FULL_MASK, my_klo, 0);
-            int cnt = 1;
-#pragma unroll
-            for (int j = 1; j < EG; ++j) {
-                const int kj = __shfl_sync(ADK_FULL_MASK, my_klo, j);
-                if (cnt == j && e0 + j < deg && kj >= klo0 && kj - klo0 + NTAPS <= 32) cnt = j + 1;
-            }
-            const int U = __shfl_sync(ADK_FULL_MASK, my_klo, cnt - 1) - klo0 + NTAPS;
-            float gv[EG];
-            const float mu = s_mu[min(klo0 + lane, R - 1)];
-#pragma unroll
-            for (int j = 0; j < EG; ++j) {
-                const float sj = __shfl_sync(ADK_FULL_MASK, my_s, j);
-                const float ej = __shfl_sync(ADK_FULL_MASK, my_env, j);
-                const float diff = sj - mu;
-                gv[j] = (j < cnt && lane < U) ? ej * expf(P.coeff * (diff * diff)) : 0.0f;
-            }
-            __syncwarp();
-            s_g[lane] = make_float4(gv[0], gv[1], gv[2], gv[3]);
-            __syncwarp();
-
-            float rb[EG][3];
-#pragma unroll
-            for (int j = 0; j < EG; ++j)
-#pragma unroll
-                for (int g = 0; g < 3; ++g) rb[j][g] = bias[g];
-            const float* wrow = s_w + (size_t)klo0 * 3 * SF + lane;
-#pragma unroll 4
-            for (int m = 0; m < U; ++m) {
-                const float4 g4 = s_g[m];
-                const float gj[EG] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    const float w = wrow[(m * 3 + g) * SF];
-#pragma unroll
-                    for (int j = 0; j < EG; ++j) rb[j][g] = fmaf(w, gj[j], rb[j][g]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < EG; ++j) {
-                if (j < cnt) {
-                    const int src = __shfl_sync(ADK_FULL_MASK, my_src, j);
-                    const float rh[3] = {__shfl_sync(ADK_FULL_MASK, my_geo.y, j), __shfl_sync(ADK_FULL_MASK, my_geo.z, j),
-                                         __shfl_sync(ADK_FULL_MASK, my_geo.w, j)};
-                    const float* xs = s_xh + (size_t)src * 3 * SF + lane;
-                    dx += xs[0] * rb[j][0];
-                    const float m2 = xs[SF] * rb[j][1] * inv_sqrt_3;
-                    const float m3 = xs[2 * SF] * rb[j][2];
-                    if (has_vec) {
-                        const float* vs = s_vec + (size_t)src * 3 * SF + lane;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) dv[c] += (vs[c * SF] * m2 + m3 * rh[c]) * inv_sqrt_h;
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) dv[c] += (m3 * rh[c]) * inv_sqrt_h;
-                    }
-                }
-            }
-            e0 += cnt;
-        }
-        float* xo = P.x_io + (size_t)t * F + f0 + lane;
-        *xo = (*xo + dx) * 0.70710678118654752440f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float base = has_vec ? s_vec[((size_t)tl * 3 + c) * SF + lane] : 0.f;
-            P.vec_out[(size_t)t * 3 * F + c * F + f0 + lane] = base + dv[c];
-        }
-    }
-}
-
 }  // namespace
 
 extern "C" int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
                            const float* e_geo, const float* xh, const float* vec_in, const float* w_rbf,
                            const float* b_rbf, const float* rbf_offset, int N, int F, int R, float cutoff,
-                           int envelope_exponent, float* x_io, float* vec_out, const int32_t* atom_off, int B,
-                           int n_max, void* stream) {
+                           int envelope_exponent, float* x_io, float* vec_out, void* stream) {
     if (!row_start || !row_deg || !e_src || !e_geo || !xh || !w_rbf || !b_rbf || !rbf_offset || !x_io ||
         !vec_out || N <= 0)
         return ADK_EINVAL;
@@ -392,14 +239,6 @@ extern "C" int adk_message(const int32_t* row_start, const int32_t* row_deg, con
     P.env_b = (float)(p * (p + 2));
     P.env_c = (float)(-p * (p + 1) / 2);
     P.x_io = x_io; P.vec_out = vec_out;
-    P.atom_off = atom_off; P.n_max = n_max;
-    if (atom_off && B > 0 && n_max > 0 && F % SF == 0 && sys_smem_bytes(R, n_max) <= 227 * 1024) {
-        // staged variant: one CTA per (system, 32-feature slice)
-        dim3 grid(B, F / SF);
-        message_sys_kernel<<<grid, SY_THREADS, sys_smem_bytes(R, n_max), adk::as_stream(stream)>>>(P);
-        ADK_LAUNCH_CHECK();
-        return 0;
-    }
     const size_t smem = sizeof(float) * ((size_t)R * 3 * FS + ((R + 3) & ~3)) + sizeof(float4) * 32 * MS_WARPS;
     dim3 grid((N + ROWS_PER_CTA - 1) / ROWS_PER_CTA, F / FS);
     message_kernel<<<grid, MS_THREADS, smem, adk::as_stream(stream)>>>(P);
@@ -408,7 +247,5 @@ extern "C" int adk_message(const int32_t* row_start, const int32_t* row_deg, con
 }
 
 int adk_message_set_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(message_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    return (int)cudaFuncSetAttribute(message_sys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return (int)cudaFuncSetAttribute(message_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 }

@@ -209,7 +209,6 @@ class PaiNN(nn.Module):
         self._plan_cache: Optional[_Plan] = None
         # "tc": tcgen05 fp16x2-split GEMMs (fp32 parity, see csrc/linear_tc.cu); "fp32": exact-fp32 SIMT GEMMs
         self.gemm = "tc"
-        self.msg_staged = False  # per-system shared-memory staging variant of the SIMT message kernel
         # message kernel: "mma" = per-system staged, rbf_proj as warp-level mma.sync micro-GEMMs
         # (csrc/message_mma.cu); "simt" = 16-tap FFMA2 kernel (csrc/message.cu); "tc" = tcgen05 experiment
         # (csrc/message_tc.cu, parity-green but gather-latency bound)
@@ -512,7 +511,7 @@ class PaiNN(nn.Module):
                 call("adk_message", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(p.xh),
                      ptr(vin) if vin is not None else None, ptr(m.rbf_proj.weight), ptr(m.rbf_proj.bias),
                      ptr(self.radial_basis.rbf.offset), N, F, R, float(self.cutoff), self.radial_basis.exponent,
-                     ptr(p.x), ptr(vout), ptr(p.atom_off) if self.msg_staged else None, p.B, p.n_max)
+                     ptr(p.x), ptr(vout))
             cur = 1 - cur
             vec = p.vec[cur]
             if trace is not None:

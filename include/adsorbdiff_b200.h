@@ -153,14 +153,12 @@ int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, const void* 
  *   w_rbf[3F][R], b_rbf[3F], rbf_offset[R] (Gaussian centres in scaled distance), R = num_rbf
  *   x_io[N][F]: in = x, out = (x + dx)/sqrt(2);  vec_out[N][3][F] = vec_in + dvec
  *   (vec_out must not alias vec_in: other rows still read it).
- *   atom_off[B+1] / n_max: system segmentation; when given (and a system's feature slices fit shared
- *   memory) each CTA stages one system's xh/vec slices and gathers from shared memory instead of L2.
+ * Row-tiled SIMT kernel, no per-system staging: the path for systems too large for adk_message_mma.
  */
 int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
                 const float* e_geo, const float* xh, const float* vec_in, const float* w_rbf,
                 const float* b_rbf, const float* rbf_offset, int N, int F, int R, float cutoff,
-                int envelope_exponent, float* x_io, float* vec_out,
-                const int32_t* atom_off, int B, int n_max, void* stream);
+                int envelope_exponent, float* x_io, float* vec_out, void* stream);
 
 /*
  * Tensor-core variant of adk_message: same contract, rbf_proj runs on tcgen05 (fp16x2 split, TMEM
