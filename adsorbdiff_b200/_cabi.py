@@ -49,9 +49,9 @@ SIGNATURES = {
     "adk_message_mma": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_int, c_int,
                                 c_float, c_int, c_float, _P, _P, _P, c_int64, c_float, _P, _P]),
     "adk_update_prep": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int64, c_float, _P, _P]),
-    "adk_update_gate": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
+    "adk_update_gate": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int64, c_float, _P, _P]),
     "adk_head_prep": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int64, c_float, _P, _P]),
-    "adk_head_gate": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
+    "adk_head_gate": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int64, c_float, _P, _P]),
     "adk_init_placement": (c_int, [_P, _P, _P, _P, _P, c_int, _P]),
     "adk_se3_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
 }

@@ -109,7 +109,8 @@ __global__ void update_prep_kernel(const float* __restrict__ x, const float* __r
 
 __global__ void update_gate_kernel(const float* __restrict__ h, const float* __restrict__ dot,
                                    const float* __restrict__ vp, const float* __restrict__ scale, int N, int F,
-                                   float* __restrict__ x, float* __restrict__ vec) {
+                                   float* __restrict__ x, float* __restrict__ vec, __half* __restrict__ vsp,
+                                   int64_t vplane, float vsp_scale, uint32_t* status) {
     const int F4 = F >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)N * F4) return;
@@ -128,13 +129,16 @@ __global__ void update_gate_kernel(const float* __restrict__ h, const float* __r
     *reinterpret_cast<float4*>(x + xo) = xn;
     const float* r = vp + (int64_t)nidx * 3 * 2 * F + f;
     float* v = vec + (int64_t)nidx * 3 * F + f;
+    bool overflow = false;
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) {
         const float4 v1 = *reinterpret_cast<const float4*>(r + cc * 2 * F);
         float4 vv = *reinterpret_cast<float4*>(v + cc * F);
         vv.x += c.x * v1.x; vv.y += c.y * v1.y; vv.z += c.z * v1.z; vv.w += c.w * v1.w;
         *reinterpret_cast<float4*>(v + cc * F) = vv;
+        if (vsp) store_split4(vsp, vplane, ((int64_t)nidx * 3 + cc) * F + f, vv, vsp_scale, overflow);
     }
+    if (overflow && status) atomicOr(status, ADK_STATUS_F16_OVERFLOW);
 }
 
 __global__ void head_prep_kernel(const float* __restrict__ x, const float* __restrict__ v1p, int N, int C,
@@ -167,7 +171,8 @@ __global__ void head_prep_kernel(const float* __restrict__ x, const float* __res
 // VEC = 4 when Co % 4 == 0 (the F/2-wide first block), 1 for the single output column of the last block
 template <int VEC>
 __global__ void head_gate_kernel(const float* __restrict__ u, const float* __restrict__ v2p, int N, int Co,
-                                 float* __restrict__ x_out, float* __restrict__ v_out) {
+                                 float* __restrict__ x_out, float* __restrict__ v_out, __half* __restrict__ vsp,
+                                 int64_t vplane, float vsp_scale, uint32_t* status) {
     const int CV = Co / VEC;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)N * CV) return;
@@ -176,6 +181,7 @@ __global__ void head_gate_kernel(const float* __restrict__ u, const float* __res
     const float* r = v2p + (int64_t)nidx * 3 * Co + f;
     float* v = v_out + (int64_t)nidx * 3 * Co + f;
     if (VEC == 4) {
+        bool overflow = false;
         const float4 s4 = *reinterpret_cast<const float4*>(ur), g = *reinterpret_cast<const float4*>(ur + Co);
         if (x_out)
             *reinterpret_cast<float4*>(x_out + (int64_t)nidx * Co + f) =
@@ -183,8 +189,11 @@ __global__ void head_gate_kernel(const float* __restrict__ u, const float* __res
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float4 rv = *reinterpret_cast<const float4*>(r + c * Co);
-            *reinterpret_cast<float4*>(v + c * Co) = make_float4(g.x * rv.x, g.y * rv.y, g.z * rv.z, g.w * rv.w);
+            const float4 o = make_float4(g.x * rv.x, g.y * rv.y, g.z * rv.z, g.w * rv.w);
+            *reinterpret_cast<float4*>(v + c * Co) = o;
+            if (vsp) store_split4(vsp, vplane, ((int64_t)nidx * 3 + c) * Co + f, o, vsp_scale, overflow);
         }
+        if (overflow && status) atomicOr(status, ADK_STATUS_F16_OVERFLOW);
     } else {
         const float s1 = ur[0], g = ur[Co];
         if (x_out) x_out[(int64_t)nidx * Co + f] = adk::ssilu(s1);
@@ -228,10 +237,13 @@ extern "C" int adk_update_prep(const float* x, const float* vp, int N, int F, fl
 }
 
 extern "C" int adk_update_gate(const float* h, const float* dot, const float* vp, const float* scale, int N,
-                               int F, float* x, float* vec, void* stream) {
-    if (!h || !dot || !vp || !scale || !x || !vec || N <= 0 || F <= 0 || (F & 3)) return ADK_EINVAL;
-    update_gate_kernel<<<blocks_for((int64_t)N * (F >> 2), 256), 256, 0, adk::as_stream(stream)>>>(h, dot, vp, scale, N, F,
-                                                                                         x, vec);
+                               int F, float* x, float* vec, void* vec_split, int64_t split_rows, float split_scale,
+                               uint32_t* status, void* stream) {
+    if (!h || !dot || !vp || !scale || !x || !vec || N <= 0 || F <= 0 || (F & 3) ||
+        (vec_split && split_rows < 3 * (int64_t)N))
+        return ADK_EINVAL;
+    update_gate_kernel<<<blocks_for((int64_t)N * (F >> 2), 256), 256, 0, adk::as_stream(stream)>>>(
+        h, dot, vp, scale, N, F, x, vec, reinterpret_cast<__half*>(vec_split), split_rows * (int64_t)F, split_scale, status);
     ADK_LAUNCH_CHECK();
     return 0;
 }
@@ -246,12 +258,16 @@ extern "C" int adk_head_prep(const float* x, const float* v1p, int N, int C, flo
 }
 
 extern "C" int adk_head_gate(const float* u, const float* v2p, int N, int Co, float* x_out, float* v_out,
-                             void* stream) {
-    if (!u || !v2p || !v_out || N <= 0 || Co <= 0) return ADK_EINVAL;
+                             void* v_split, int64_t split_rows, float split_scale, uint32_t* status, void* stream) {
+    if (!u || !v2p || !v_out || N <= 0 || Co <= 0 || (v_split && ((Co & 3) || split_rows < 3 * (int64_t)N))) return ADK_EINVAL;
+    __half* vsp = reinterpret_cast<__half*>(v_split);
+    const int64_t plane = split_rows * (int64_t)Co;
     if ((Co & 3) == 0)
-        head_gate_kernel<4><<<blocks_for((int64_t)N * (Co >> 2), 256), 256, 0, adk::as_stream(stream)>>>(u, v2p, N, Co, x_out, v_out);
+        head_gate_kernel<4><<<blocks_for((int64_t)N * (Co >> 2), 256), 256, 0, adk::as_stream(stream)>>>(
+            u, v2p, N, Co, x_out, v_out, vsp, plane, split_scale, status);
     else
-        head_gate_kernel<1><<<blocks_for((int64_t)N * Co, 256), 256, 0, adk::as_stream(stream)>>>(u, v2p, N, Co, x_out, v_out);
+        head_gate_kernel<1><<<blocks_for((int64_t)N * Co, 256), 256, 0, adk::as_stream(stream)>>>(
+            u, v2p, N, Co, x_out, v_out, nullptr, 0, 0.f, status);
     ADK_LAUNCH_CHECK();
     return 0;
 }

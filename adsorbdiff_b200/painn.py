@@ -456,14 +456,16 @@ class PaiNN(nn.Module):
         call("adk_head_prep", dev, ptr(x), ptr(p.v1p), N, F, None if tc else ptr(p.cat), ptr(p.sp_x) if tc else None,
              p.rows_n, self.A_SCALE, ptr(p.status))
         self._mlp2(p, p.cat, 2 * F, N, 2 * F, b0.update_net[0], b0.update_net[2], p.xn, F, presplit=tc)  # (s|g)
-        call("adk_head_gate", dev, ptr(p.xn), ptr(p.v2p), N, H, ptr(p.hx), ptr(p.hv))
+        hv_tc = any(self._tc_ok(l) for l in (b1.vec1_proj, b1.vec2_proj)) and H % 4 == 0
+        call("adk_head_gate", dev, ptr(p.xn), ptr(p.v2p), N, H, ptr(p.hx), ptr(p.hv),
+             ptr(p.sp_hv) if hv_tc else None, p.rows_3n, self.V_SCALE, ptr(p.status))
         # block 1: H -> 1
-        self._vec_linear(p, p.hv, H, [(b1.vec1_proj, p.v1p), (b1.vec2_proj, p.v2p2)], planes=p.sp_hv)
+        self._vec_linear(p, p.hv, H, [(b1.vec1_proj, p.v1p), (b1.vec2_proj, p.v2p2)], presplit=hv_tc, planes=p.sp_hv)
         tc = self._tc_ok(b1.update_net[0])
         call("adk_head_prep", dev, ptr(p.hx), ptr(p.v1p), N, H, None if tc else ptr(p.cat), ptr(p.sp_x) if tc else None,
              p.rows_n, self.A_SCALE, ptr(p.status))
         self._mlp2(p, p.cat, 2 * H, N, 2 * H, b1.update_net[0], b1.update_net[2], p.ho2, 2, presplit=tc)
-        call("adk_head_gate", dev, ptr(p.ho2), ptr(p.v2p2), N, 1, None, ptr(out))
+        call("adk_head_gate", dev, ptr(p.ho2), ptr(p.v2p2), N, 1, None, ptr(out), None, 0, 0.0, ptr(p.status))
 
     def _run(self, p: _Plan, z: torch.Tensor, pos: torch.Tensor, trace: Optional[dict] = None,
              weights_ready: bool = False):
@@ -480,6 +482,7 @@ class PaiNN(nn.Module):
         call("adk_embed", dev, ptr(z), ptr(self.atom_emb.embeddings.weight), self.atom_emb.embeddings.weight.shape[0],
              N, F, ptr(p.x), None)
         cur = 0
+        heads_presplit = False
         for l in range(self.num_layers):
             m, u = self.message_layers[l], self.update_layers[l]
             tc = self._tc_ok(m.x_proj[0])
@@ -522,19 +525,25 @@ class PaiNN(nn.Module):
                  ptr(p.sp_x) if tc else None, p.rows_n, self.A_SCALE, ptr(p.status))
             self._mlp2(p, p.cat, 2 * F, N, 2 * F, u.xvec_proj[0], u.xvec_proj[2], p.xh, 3 * F, presplit=tc)
             sc = getattr(self, "upd_out_scalar_scale_%d" % l).scale_factor
-            call("adk_update_gate", dev, ptr(p.xh), ptr(p.dot), ptr(p.vp), ptr(sc), N, F, ptr(p.x), ptr(vec))
+            # the last layer's update also writes the fp16x2 planes of vec that both heads' vec projections read
+            b0 = self.out_forces.output_network[0]
+            emit = l == self.num_layers - 1 and any(self._tc_ok(q) for q in (b0.vec1_proj, b0.vec2_proj))
+            call("adk_update_gate", dev, ptr(p.xh), ptr(p.dot), ptr(p.vp), ptr(sc), N, F, ptr(p.x), ptr(vec),
+                 ptr(p.sp_v) if emit else None, p.rows_3n, self.V_SCALE, ptr(p.status))
+            heads_presplit = emit
             if trace is not None:
                 trace[f"upd{l}.x"], trace[f"upd{l}.vec"] = p.x.clone(), vec.clone()
         vec = p.vec[cur]
         saved_gemm = self.gemm
         self.gemm = getattr(self, "gemm_heads", None) or saved_gemm
         try:
-            self._head(p, self.out_forces, p.x, vec, p.out[0], presplit=False)
+            # (gemm_heads may differ from the trunk's engine: then the planes are split here instead)
+            b0 = self.out_forces.output_network[0]
+            need = any(self._tc_ok(q) for q in (b0.vec1_proj, b0.vec2_proj))
+            self._head(p, self.out_forces, p.x, vec, p.out[0], presplit=heads_presplit and need)
             if self.so3_denoising:
-                # the first head split `vec` into p.sp_v (its hidden channel has planes of its own): reuse them
-                b0 = self.out_forces.output_network[0]
-                self._head(p, self.out_forces2, p.x, vec, p.out[1],
-                           presplit=any(self._tc_ok(l) for l in (b0.vec1_proj, b0.vec2_proj)))
+                # p.sp_v still holds the planes of vec (the heads' hidden channel has planes of its own)
+                self._head(p, self.out_forces2, p.x, vec, p.out[1], presplit=need)
         finally:
             self.gemm = saved_gemm
 

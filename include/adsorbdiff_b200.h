@@ -204,7 +204,9 @@ int adk_update_prep(const float* x, const float* vp, int N, int F, float* dot, f
  * PaiNNUpdate.forward (:614-623), PaiNN.forward (:449-451), ScaleFactor.forward
  * (modules/scaling/scale_factor.py:157-172; scale == 0 means "not fitted": no multiply). */
 int adk_update_gate(const float* h, const float* dot, const float* vp, const float* scale /* device scalar */,
-                    int N, int F, float* x, float* vec, void* stream);
+                    int N, int F, float* x, float* vec,
+                    void* vec_split /* fp16 [2][split_rows][F] planes of the new vec (row = atom*3+xyz), or NULL */,
+                    int64_t split_rows, float split_scale, uint32_t* status, void* stream);
 
 /* GatedEquivariantBlock (painn_denoising.py:688-697), the parts around its linears:
  * prep: cat[N][2C] = [x | ||v1p||_xyz] from v1p[N][3][C] = vec1_proj(v);
@@ -212,7 +214,9 @@ int adk_update_gate(const float* h, const float* dot, const float* vp, const flo
 int adk_head_prep(const float* x, const float* v1p, int N, int C, float* cat /* may be NULL */,
                   void* cat_split /* fp16 [2][split_rows][2C] or NULL */, int64_t split_rows, float split_scale,
                   uint32_t* status, void* stream);
-int adk_head_gate(const float* u, const float* v2p, int N, int Co, float* x_out, float* v_out, void* stream);
+int adk_head_gate(const float* u, const float* v2p, int N, int Co, float* x_out, float* v_out,
+                  void* v_split /* fp16 [2][split_rows][Co] planes of v_out, Co % 4 == 0, or NULL */, int64_t split_rows,
+                  float split_scale, uint32_t* status, void* stream);
 
 /*
  * Initial placement: random in-plane centre of mass for the adsorbate (tags == 2), z kept.
