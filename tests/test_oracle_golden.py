@@ -59,21 +59,30 @@ def test_empty_system_raises(golden):
         O.generate_graph_values(b.pos.numpy(), b.cell.numpy(), b.natoms)
 
 
+# Two tolerances.  The fp32 evaluation of the oracle repeats the reference's arithmetic, but torch's CPU GEMMs /
+# reductions pick their summation order by core count and ISA: on the host that generated the fixtures the two agree
+# to 2e-6, another host measured 2.4e-5.  The fp64 evaluation does not depend on the host and sits at the reference's
+# own fp32 rounding error (3-5e-6) from the frozen output; any algorithmic slip is orders of magnitude larger.
+FP32_HOST_TOL = 5e-5
+FP64_TOL = 1e-5
+
+
 @pytest.mark.parametrize("name", ["jit2", "mixed", "tiny", "gas"])
 def test_forward_matches_reference(name, golden, weights):
     make, pbc = CASES[name]
     b, g = make(), golden(name)
-    tr = {}
-    f1, f2 = O.painn_forward(weights, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms,
-                             pbc=pbc or (True, True, True), trace=tr)
-    for out, key in ((f1, "forces"), (f2, "forces2")):
-        ref = g[key]
-        assert np.abs(out.numpy() - ref).max() <= 2e-6 * np.abs(ref).max() + 1e-9
     rows = g["rows"]
-    for k in g.files:
-        if k[:3] in ("msg", "upd"):
-            ref = g[k]
-            assert np.abs(tr[k][rows].numpy() - ref).max() <= 2e-6 * np.abs(ref).max(), k
+    for dtype, tol in ((torch.float32, FP32_HOST_TOL), (torch.float64, FP64_TOL)):
+        tr = {}
+        f1, f2 = O.painn_forward(weights, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms,
+                                 pbc=pbc or (True, True, True), trace=tr, dtype=dtype)
+        for out, key in ((f1, "forces"), (f2, "forces2")):
+            ref = g[key]
+            assert np.abs(out.numpy() - ref).max() <= tol * np.abs(ref).max() + 1e-9, (key, dtype)
+        for k in g.files:
+            if k[:3] in ("msg", "upd"):
+                ref = g[k]
+                assert np.abs(tr[k][rows].numpy() - ref).max() <= tol * np.abs(ref).max(), (k, dtype)
 
 
 def test_sampler_matches_reference(golden, sampler_weights):
@@ -87,4 +96,4 @@ def test_sampler_matches_reference(golden, sampler_weights):
     steps = 3  # CPU-suite budget: three reference steps pin init + schedule + SE(3) update
     O.sample(weights, fields, params, torch.from_numpy(g["noise"]), num_steps=steps, record=rec)
     for t in range(steps):
-        np.testing.assert_allclose(rec[t].numpy(), g["traj"][t], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(rec[t].numpy(), g["traj"][t], rtol=0, atol=1e-4)  # Angstrom; host-dependent fp32 noise x step gain
