@@ -61,7 +61,8 @@ struct MmParams {
 };
 
 __host__ __device__ inline size_t mm_smem_bytes(int R, int n_max) {
-    return 2 * (size_t)R * MM_WROW + sizeof(float) * ((size_t)R + 96) + sizeof(float) * (size_t)n_max * 2 * MM_SRC_STRIDE + 64;
+    return 2 * (size_t)R * MM_WROW + sizeof(float) * ((size_t)R + 96) + sizeof(float) * (size_t)n_max * 2 * MM_SRC_STRIDE +
+           (((size_t)n_max * 2 + 15) & ~(size_t)15) + 64;   // + row order (int16) + row counter / slack
 }
 
 // the column offset is an immediate of the instruction: one address register per (k-step, plane) instead of six
@@ -110,6 +111,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     float* s_bias = s_mu + R;                                        // [3][qt 4][nt 4][2], same order as a source row
     float* s_xh = s_bias + 96;                                       // [n][MM_SRC_STRIDE]
     float* s_vec = s_xh + (size_t)P.n_max * MM_SRC_STRIDE;           // [n][MM_SRC_STRIDE]
+    int16_t* s_order = reinterpret_cast<int16_t*>(s_vec + (size_t)P.n_max * MM_SRC_STRIDE);   // rows, longest first
+    int* s_next = reinterpret_cast<int*>(s_order + ((P.n_max + 7) & ~7));                   // next unclaimed position
     const int b = blockIdx.x, f0 = blockIdx.y * MM_SF;
     const int a0 = P.atom_off[b], n = P.atom_off[b + 1] - a0;
     const int lane = adk::lane_id(), warp = adk::warp_id();
@@ -147,6 +150,18 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
                              : "memory");
         }
     }
+    // Rows are claimed dynamically, longest first (LPT): with 12 warps and ~82 rows of 3-4 chunks each a fixed
+    // round-robin leaves the slowest warp ~5 % behind the mean.  Rank by (degree desc, index asc): a permutation.
+    for (int r = threadIdx.x; r < n; r += MM_THREADS) {
+        const int dr = P.row_deg[a0 + r];
+        int rank = 0;
+        for (int u = 0; u < n; ++u) {
+            const int du = P.row_deg[a0 + u];
+            rank += (du > dr || (du == dr && u < r)) ? 1 : 0;
+        }
+        s_order[rank] = (int16_t)r;
+    }
+    if (threadIdx.x == 0) *s_next = 0;
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -163,7 +178,12 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     const float inv_sqrt_h = 0.57735026918962576451f / sqrtf((float)F);   // includes the 1/sqrt(3) of x_ij2
 
     // gridDim.z > 1 (a handful of systems only): the target rows of a system are dealt to several CTAs
-    for (int tl = warp + MM_WARPS * blockIdx.z; tl < n; tl += MM_WARPS * gridDim.z) {
+    while (true) {
+        int claim = 0;
+        if (lane == 0) claim = atomicAdd(s_next, 1);
+        claim = __shfl_sync(ADK_FULL_MASK, claim, 0) * (int)gridDim.z + (int)blockIdx.z;
+        if (claim >= n) break;
+        const int tl = s_order[claim];
         const int t = a0 + tl;
         const int start = P.row_start[t], deg = P.row_deg[t];
         float dxa[4][2], dva[3][4][2];
