@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
     with open(stamp, "w") as f:
         f.write(digest)
