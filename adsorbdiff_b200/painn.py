@@ -333,6 +333,14 @@ class PaiNN(nn.Module):
         p.sp_v = torch.zeros(2 * p.rows_3n * F, **f16)        # vec-wise inputs, K <= F
         p.sp_hv = torch.zeros(2 * p.rows_3n * (F // 2), **f16)  # the heads' hidden vec channel, K = F/2
         p.wt_rbf = [torch.empty(2 * self.num_rbf * 3 * F, **f16) for _ in range(self.num_layers)]
+        # layer 0 evaluates LayerNorm + x_proj once per element on the embedding table (see _run)
+        ne = self.atom_emb.embeddings.weight.shape[0]
+        p.tab_rows = pad(ne)
+        p.tab_y = torch.empty(ne, F, **f32)
+        p.tab_h1 = torch.empty(ne, F, **f32)
+        p.tab_xh = torch.empty(ne, 3 * F, **f32)
+        p.tab_spx = torch.zeros(2 * p.tab_rows * F, **f16)
+        p.tab_sph = torch.zeros(2 * p.tab_rows * F, **f16)
         # does a system's staged slice fit the shared memory of the warp-MMA message kernel?  (else: adk_message)
         p.mma_fits = (self.num_rbf % 16 == 0 and 16 <= self.num_rbf <= 128
                       and _cabi.load().adk_message_mma_smem_bytes(self.num_rbf, p.n_max) > 0)
@@ -414,23 +422,24 @@ class PaiNN(nn.Module):
              ptr(out_f32) if out_f32 is not None else None, ldc,
              ptr(out_split) if out_split is not None else None, out_rows, self.A_SCALE, ptr(p.status))
 
-    def _mlp2(self, p, A, lda, M, K, lin0, lin1, out, ldc, presplit=False):
+    def _mlp2(self, p, A, lda, M, K, lin0, lin1, out, ldc, presplit=False, ws=None):
         """out = lin1(ssilu(lin0(A))): the two-layer MLP shape shared by x_proj, xvec_proj and update_net.
-        `presplit`: the producer kernel already wrote the fp16x2 planes of A into p.sp_x."""
+        `presplit`: the producer kernel already wrote the fp16x2 planes of A into the input planes.
+        `ws` = (input planes, hidden planes, plane rows, fp32 hidden) when not the per-atom workspaces."""
+        sp_in, sp_hid, rows, h1 = ws if ws is not None else (p.sp_x, p.sp_h, p.rows_n, p.h1)
         if self._tc_ok(lin0):
-            rows = p.rows_n
             if not presplit:
-                self._split(p, A, lda, M, K, p.sp_x, rows)
+                self._split(p, A, lda, M, K, sp_in, rows)
             if self._tc_ok(lin1):
-                self._linear_tc(p, p.sp_x, rows, M, lin0, _cabi.ACT_SSILU, out_split=p.sp_h, out_rows=rows)
-                self._linear_tc(p, p.sp_h, rows, M, lin1, _cabi.ACT_NONE, out_f32=out, ldc=ldc)
+                self._linear_tc(p, sp_in, rows, M, lin0, _cabi.ACT_SSILU, out_split=sp_hid, out_rows=rows)
+                self._linear_tc(p, sp_hid, rows, M, lin1, _cabi.ACT_NONE, out_f32=out, ldc=ldc)
             else:
-                self._linear_tc(p, p.sp_x, rows, M, lin0, _cabi.ACT_SSILU, out_f32=p.h1, ldc=lin0.weight.shape[0])
-                self._linear(p, p.h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
+                self._linear_tc(p, sp_in, rows, M, lin0, _cabi.ACT_SSILU, out_f32=h1, ldc=lin0.weight.shape[0])
+                self._linear(p, h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
         else:
             assert not presplit, "producer must hand an fp32 operand to the SIMT path"
-            self._linear(p, A, lda, lin0, M, _cabi.ACT_SSILU, p.h1, lin0.weight.shape[0])
-            self._linear(p, p.h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
+            self._linear(p, A, lda, lin0, M, _cabi.ACT_SSILU, h1, lin0.weight.shape[0])
+            self._linear(p, h1, lin0.weight.shape[0], lin1, M, _cabi.ACT_NONE, out, ldc)
 
     def _vec_linear(self, p, vec, K, lins_outs, presplit=False, planes=None):
         """vec-wise bias-free projections of [3N, K] (vec_proj, vec1_proj, vec2_proj); one split feeds all."""
@@ -486,10 +495,23 @@ class PaiNN(nn.Module):
         for l in range(self.num_layers):
             m, u = self.message_layers[l], self.update_layers[l]
             tc = self._tc_ok(m.x_proj[0])
-            call("adk_layernorm", dev, ptr(p.x), ptr(m.x_layernorm.weight), ptr(m.x_layernorm.bias), N, F,
-                 float(m.x_layernorm.eps), None if tc else ptr(p.xn), ptr(p.sp_x) if tc else None, p.rows_n,
-                 self.A_SCALE, ptr(p.status))
-            self._mlp2(p, p.xn, F, N, F, m.x_proj[0], m.x_proj[2], p.xh, 3 * F, presplit=tc)
+            if l == 0:
+                # x = emb[z - 1], so layer 0's LayerNorm + x_proj is a function of the element alone: evaluate it on
+                # the embedding table (83 rows instead of N; same kernels, so every row is bit-identical to the
+                # per-atom evaluation) and gather the rows by atomic number.
+                E = self.atom_emb.embeddings.weight
+                ne = E.shape[0]
+                call("adk_layernorm", dev, ptr(E), ptr(m.x_layernorm.weight), ptr(m.x_layernorm.bias), ne, F,
+                     float(m.x_layernorm.eps), None if tc else ptr(p.tab_y), ptr(p.tab_spx) if tc else None, p.tab_rows,
+                     self.A_SCALE, ptr(p.status))
+                self._mlp2(p, p.tab_y, F, ne, F, m.x_proj[0], m.x_proj[2], p.tab_xh, 3 * F, presplit=tc,
+                           ws=(p.tab_spx, p.tab_sph, p.tab_rows, p.tab_h1))
+                call("adk_embed", dev, ptr(z), ptr(p.tab_xh), ne, N, 3 * F, ptr(p.xh), None)
+            else:
+                call("adk_layernorm", dev, ptr(p.x), ptr(m.x_layernorm.weight), ptr(m.x_layernorm.bias), N, F,
+                     float(m.x_layernorm.eps), None if tc else ptr(p.xn), ptr(p.sp_x) if tc else None, p.rows_n,
+                     self.A_SCALE, ptr(p.status))
+                self._mlp2(p, p.xn, F, N, F, m.x_proj[0], m.x_proj[2], p.xh, 3 * F, presplit=tc)
             vin = p.vec[cur] if l > 0 else None  # vec == 0 before the first message
             vout = p.vec[1 - cur]
             vec_presplit = False
