@@ -39,6 +39,7 @@ constexpr int MM_SRC_STRIDE = 112;
 
 struct MmParams {
     const int32_t* atom_off;
+    const int32_t* row_sel;     // optional [N] flags: only rows with a non-zero flag are computed and written
     const int32_t* row_start;
     const int32_t* row_deg;
     const int32_t* e_src;
@@ -153,15 +154,22 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     // Rows are claimed dynamically, longest first (LPT): with 12 warps and ~82 rows of 3-4 chunks each a fixed
     // round-robin leaves the slowest warp ~5 % behind the mean.  Rank by (degree desc, index asc): a permutation.
     for (int r = threadIdx.x; r < n; r += MM_THREADS) {
+        if (P.row_sel && P.row_sel[a0 + r] == 0) continue;
         const int dr = P.row_deg[a0 + r];
         int rank = 0;
         for (int u = 0; u < n; ++u) {
+            if (P.row_sel && P.row_sel[a0 + u] == 0) continue;
             const int du = P.row_deg[a0 + u];
             rank += (du > dr || (du == dr && u < r)) ? 1 : 0;
         }
         s_order[rank] = (int16_t)r;
     }
-    if (threadIdx.x == 0) *s_next = 0;
+    if (threadIdx.x < 32) {   // warp 0: number of selected rows, claim counter
+        int c = 0;
+        for (int r = threadIdx.x; r < n; r += 32) c += (!P.row_sel || P.row_sel[a0 + r] != 0) ? 1 : 0;
+        c = __reduce_add_sync(ADK_FULL_MASK, c);
+        if (threadIdx.x == 0) { s_next[0] = 0; s_next[1] = c; }
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -178,11 +186,12 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     const float inv_sqrt_h = 0.57735026918962576451f / sqrtf((float)F);   // includes the 1/sqrt(3) of x_ij2
 
     // gridDim.z > 1 (a handful of systems only): the target rows of a system are dealt to several CTAs
+    const int n_rows = s_next[1];
     while (true) {
         int claim = 0;
         if (lane == 0) claim = atomicAdd(s_next, 1);
         claim = __shfl_sync(ADK_FULL_MASK, claim, 0) * (int)gridDim.z + (int)blockIdx.z;
-        if (claim >= n) break;
+        if (claim >= n_rows) break;
         const int tl = s_order[claim];
         const int t = a0 + tl;
         const int start = P.row_start[t], deg = P.row_deg[t];
@@ -511,7 +520,7 @@ extern "C" int64_t adk_message_mma_smem_bytes(int R, int n_max) {
     return b > 227 * 1024 ? (int64_t)ADK_ERANGE : (int64_t)b;
 }
 
-extern "C" int adk_message_mma(const int32_t* atom_off, int B, int n_max, const int32_t* row_start,
+extern "C" int adk_message_mma(const int32_t* atom_off, int B, int n_max, const int32_t* row_sel, const int32_t* row_start,
                                const int32_t* row_deg, const int32_t* e_src, const float* e_geo, const float* xh,
                                const float* vec_in, const void* wt_split, float w_scale, const float* b_rbf,
                                const float* rbf_offset, int F, int R, float cutoff, int envelope_exponent,
@@ -525,7 +534,7 @@ extern "C" int adk_message_mma(const int32_t* atom_off, int B, int n_max, const 
     const size_t smem = mm_smem_bytes(R, n_max);
     if (smem > 227 * 1024) return ADK_ERANGE;
     MmParams P;
-    P.atom_off = atom_off; P.row_start = row_start; P.row_deg = row_deg; P.e_src = e_src;
+    P.atom_off = atom_off; P.row_sel = row_sel; P.row_start = row_start; P.row_deg = row_deg; P.e_src = e_src;
     P.e_geo = reinterpret_cast<const float4*>(e_geo);
     P.xh = xh; P.vec_in = vec_in; P.wt_split = reinterpret_cast<const __half*>(wt_split);
     P.b_rbf = b_rbf; P.rbf_offset = rbf_offset;

@@ -202,6 +202,33 @@ __global__ void head_gate_kernel(const float* __restrict__ u, const float* __res
     }
 }
 
+template <bool SCATTER, typename T>   // T = float4 (W % 4 == 0) or float
+__global__ void move_rows_kernel(const T* __restrict__ src, const int32_t* __restrict__ rows, int M, int WT,
+                                 T* __restrict__ dst) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * WT) return;
+    const int i = (int)(idx / WT), c = (int)(idx - (int64_t)i * WT);
+    const int64_t r = rows[i];
+    if (SCATTER) dst[r * WT + c] = src[(int64_t)i * WT + c];
+    else dst[(int64_t)i * WT + c] = src[r * WT + c];
+}
+
+template <bool SCATTER>
+int move_rows(const float* src, const int32_t* rows, int M, int W, float* dst, void* stream) {
+    if (!src || !rows || !dst || M <= 0 || W <= 0) return ADK_EINVAL;
+    cudaStream_t st = adk::as_stream(stream);
+    if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        const int64_t n = (int64_t)M * (W >> 2);
+        move_rows_kernel<SCATTER, float4><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(src), rows, M, W >> 2, reinterpret_cast<float4*>(dst));
+    } else {
+        const int64_t n = (int64_t)M * W;
+        move_rows_kernel<SCATTER, float><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, rows, M, W, dst);
+    }
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
 inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -270,4 +297,12 @@ extern "C" int adk_head_gate(const float* u, const float* v2p, int N, int Co, fl
             u, v2p, N, Co, x_out, v_out, nullptr, 0, 0.f, status);
     ADK_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int adk_gather_rows(const float* src, const int32_t* rows, int M, int W, float* dst, void* stream) {
+    return move_rows<false>(src, rows, M, W, dst, stream);
+}
+
+extern "C" int adk_scatter_rows(const float* src, const int32_t* rows, int M, int W, float* dst, void* stream) {
+    return move_rows<true>(src, rows, M, W, dst, stream);
 }

@@ -160,8 +160,19 @@ class Denoiser:
             if record:
                 self.frames = torch.empty(num_steps, plan.N, 3, dtype=torch.float32, device=dev)
 
+            # The SE(3) update averages both scores over the adsorbate atoms and reads nothing else
+            # (reference :460-467, 322-338), and nothing after the last message layer mixes atoms: that layer's
+            # message, its update block and the heads are evaluated for the adsorbate rows only
+            # (denoising_pos_params["full_forward"] = True evaluates every atom like the reference).
+            out_rows = None
+            if not params.get("full_forward", False):
+                flags = (tags == 2).to(torch.int32).contiguous()
+                idx = torch.nonzero(flags, as_tuple=False).flatten().to(torch.int32).contiguous()
+                if 0 < idx.numel() < plan.N:
+                    out_rows = (idx, flags)
+
             def one_step(weights_ready=False):
-                net._run(plan, z, pos, weights_ready=weights_ready)
+                net._run(plan, z, pos, weights_ready=weights_ready, out_rows=out_rows)
                 call("adk_se3_step", dev, ptr(pos), ptr(plan.cell_f32), ptr(plan.atom_off), ptr(tags), ptr(fixed),
                      ptr(plan.out[0]), ptr(plan.out[1]), ptr(sched), ptr(step), B, ptr(max_upd))
 

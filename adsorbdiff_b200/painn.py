@@ -323,7 +323,7 @@ class PaiNN(nn.Module):
         p.hv = torch.empty(N, 3, H, **f32)
         p.v2p2 = torch.empty(N, 3, 1, **f32)
         p.ho2 = torch.empty(N, 2, **f32)
-        p.out = [torch.empty(N, 3, **f32), torch.empty(N, 3, **f32)]
+        p.out = [torch.zeros(N, 3, **f32), torch.zeros(N, 3, **f32)]
         # fp16x2 operand planes for the tensor-core GEMMs: [2][rows padded to 128][K]; pad rows stay zero
         pad = lambda r: (r + 127) // 128 * 128
         f16 = dict(dtype=torch.float16, device=dev)
@@ -477,12 +477,16 @@ class PaiNN(nn.Module):
         call("adk_head_gate", dev, ptr(p.ho2), ptr(p.v2p2), N, 1, None, ptr(out), None, 0, 0.0, ptr(p.status))
 
     def _run(self, p: _Plan, z: torch.Tensor, pos: torch.Tensor, trace: Optional[dict] = None,
-             weights_ready: bool = False):
+             weights_ready: bool = False, out_rows=None):
         """Enqueue the whole forward on the current stream (capturable: no sync, no allocation).
         `weights_ready`: the fp16x2 operand planes of the weights (GEMM planes and the transposed rbf_proj planes
         in this plan) were produced by an earlier `_run` and the parameters have not changed since -- only a
         caller that owns the parameters for the duration may say so (the sampler, between its EMA swap-in and
-        swap-out); `forward` never does."""
+        swap-out); `forward` never does.
+        `out_rows` = (idx int32 [Ns], flags int32 [N]): the caller reads the two outputs only at these atoms (the
+        sampler: the adsorbate).  Nothing after the last message layer mixes atoms, so that layer's message, its update
+        block and both heads are then evaluated for those rows only; `p.out` is written at `idx`, other rows keep
+        whatever they held.  The rows that are written are bit-identical to the full evaluation."""
         N, F, R = p.N, self.hidden_channels, self.num_rbf
         dev = p.device
         if (self.gemm == "tc" or self.msg == "tc") and not weights_ready:
@@ -520,12 +524,18 @@ class PaiNN(nn.Module):
                 if not weights_ready:
                     call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self.W_SCALE, ptr(wt),
                          ptr(p.status))
-                call("adk_message_mma", dev, ptr(p.atom_off), p.B, p.n_max, ptr(p.row_start), ptr(p.row_deg),
+                pruned = out_rows is not None and l == self.num_layers - 1 and trace is None
+                planes = self._tc_ok(u.vec_proj) and not pruned
+                call("adk_message_mma", dev, ptr(p.atom_off), p.B, p.n_max, ptr(out_rows[1]) if pruned else None,
+                     ptr(p.row_start), ptr(p.row_deg),
                      ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wt),
                      self.W_SCALE, ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R,
                      float(self.cutoff), self.radial_basis.exponent, float(self.msg_comp), ptr(p.x), ptr(vout),
-                     ptr(p.sp_v) if self._tc_ok(u.vec_proj) else None, p.rows_3n, self.V_SCALE, ptr(p.status))
-                vec_presplit = self._tc_ok(u.vec_proj)
+                     ptr(p.sp_v) if planes else None, p.rows_3n, self.V_SCALE, ptr(p.status))
+                vec_presplit = planes
+                if pruned:
+                    self._finish_rows(p, out_rows[0], l, vout)
+                    return
             elif self.msg == "tc" and F == 512 and R == 128:
                 wr = self._wsplit(p, m.rbf_proj)
                 call("adk_message_tc", dev, ptr(p.atom_off), p.B, ptr(p.sys_counts), ptr(p.row_deg), ptr(p.e_src),
@@ -541,21 +551,30 @@ class PaiNN(nn.Module):
             vec = p.vec[cur]
             if trace is not None:
                 trace[f"msg{l}.x"], trace[f"msg{l}.vec"] = p.x.clone(), vec.clone()
-            self._vec_linear(p, vec, F, [(u.vec_proj, p.vp)], presplit=vec_presplit)
-            tc = self._tc_ok(u.xvec_proj[0])
-            call("adk_update_prep", dev, ptr(p.x), ptr(p.vp), N, F, ptr(p.dot), None if tc else ptr(p.cat),
-                 ptr(p.sp_x) if tc else None, p.rows_n, self.A_SCALE, ptr(p.status))
-            self._mlp2(p, p.cat, 2 * F, N, 2 * F, u.xvec_proj[0], u.xvec_proj[2], p.xh, 3 * F, presplit=tc)
-            sc = getattr(self, "upd_out_scalar_scale_%d" % l).scale_factor
-            # the last layer's update also writes the fp16x2 planes of vec that both heads' vec projections read
-            b0 = self.out_forces.output_network[0]
-            emit = l == self.num_layers - 1 and any(self._tc_ok(q) for q in (b0.vec1_proj, b0.vec2_proj))
-            call("adk_update_gate", dev, ptr(p.xh), ptr(p.dot), ptr(p.vp), ptr(sc), N, F, ptr(p.x), ptr(vec),
-                 ptr(p.sp_v) if emit else None, p.rows_3n, self.V_SCALE, ptr(p.status))
-            heads_presplit = emit
+            heads_presplit = self._update(p, l, vec, vec_presplit)
             if trace is not None:
                 trace[f"upd{l}.x"], trace[f"upd{l}.vec"] = p.x.clone(), vec.clone()
-        vec = p.vec[cur]
+        self._heads(p, p.vec[cur], heads_presplit)
+
+    def _update(self, p, l: int, vec: torch.Tensor, vec_presplit: bool) -> bool:
+        """PaiNNUpdate + ScaleFactor of layer l on the rows of plan `p` (painn_denoising.py:601-623, 449-451).
+        Returns whether the fp16x2 planes of the new vec were left in p.sp_v for the heads."""
+        N, F, dev = p.N, self.hidden_channels, p.device
+        u = self.update_layers[l]
+        self._vec_linear(p, vec, F, [(u.vec_proj, p.vp)], presplit=vec_presplit)
+        tc = self._tc_ok(u.xvec_proj[0])
+        call("adk_update_prep", dev, ptr(p.x), ptr(p.vp), N, F, ptr(p.dot), None if tc else ptr(p.cat),
+             ptr(p.sp_x) if tc else None, p.rows_n, self.A_SCALE, ptr(p.status))
+        self._mlp2(p, p.cat, 2 * F, N, 2 * F, u.xvec_proj[0], u.xvec_proj[2], p.xh, 3 * F, presplit=tc)
+        sc = getattr(self, "upd_out_scalar_scale_%d" % l).scale_factor
+        # the last layer's update also writes the fp16x2 planes of vec that both heads' vec projections read
+        b0 = self.out_forces.output_network[0]
+        emit = l == self.num_layers - 1 and any(self._tc_ok(q) for q in (b0.vec1_proj, b0.vec2_proj))
+        call("adk_update_gate", dev, ptr(p.xh), ptr(p.dot), ptr(p.vp), ptr(sc), N, F, ptr(p.x), ptr(vec),
+             ptr(p.sp_v) if emit else None, p.rows_3n, self.V_SCALE, ptr(p.status))
+        return emit
+
+    def _heads(self, p, vec: torch.Tensor, heads_presplit: bool) -> None:
         saved_gemm = self.gemm
         self.gemm = getattr(self, "gemm_heads", None) or saved_gemm
         try:
@@ -568,6 +587,49 @@ class PaiNN(nn.Module):
                 self._head(p, self.out_forces2, p.x, vec, p.out[1], presplit=need)
         finally:
             self.gemm = saved_gemm
+
+    def _subplan(self, p: _Plan, ns: int) -> _Plan:
+        """Workspaces for the update block and the heads on `ns` selected rows (same attribute names as the plan)."""
+        q = getattr(p, "sub", None)
+        if q is not None and q.N == ns:
+            return q
+        F, H, dev = self.hidden_channels, self.hidden_channels // 2, p.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        f16 = dict(dtype=torch.float16, device=dev)
+        pad = lambda r: (r + 127) // 128 * 128
+        q = _Plan()
+        q.N, q.device, q.status = ns, dev, p.status
+        q.rows_n, q.rows_3n = pad(ns), pad(3 * ns)
+        q.x, q.xn, q.h1, q.dot = (torch.empty(ns, F, **f32) for _ in range(4))
+        q.xh = torch.empty(ns, 3 * F, **f32)
+        q.vecbuf = torch.empty(ns, 3, F, **f32)
+        q.vp = torch.empty(ns, 3, 2 * F, **f32)
+        q.cat = torch.empty(ns, 2 * F, **f32)
+        q.v1p = torch.empty(ns, 3, F, **f32)
+        q.v2p = torch.empty(ns, 3, H, **f32)
+        q.hx = torch.empty(ns, H, **f32)
+        q.hv = torch.empty(ns, 3, H, **f32)
+        q.v2p2 = torch.empty(ns, 3, 1, **f32)
+        q.ho2 = torch.empty(ns, 2, **f32)
+        q.out = [torch.empty(ns, 3, **f32), torch.empty(ns, 3, **f32)]
+        q.sp_x = torch.zeros(2 * q.rows_n * 2 * F, **f16)
+        q.sp_h = torch.zeros(2 * q.rows_n * F, **f16)
+        q.sp_v = torch.zeros(2 * q.rows_3n * F, **f16)
+        q.sp_hv = torch.zeros(2 * q.rows_3n * H, **f16)
+        p.sub = q
+        return q
+
+    def _finish_rows(self, p: _Plan, idx: torch.Tensor, l: int, vec: torch.Tensor) -> None:
+        """Update block of the last layer and both heads on the rows `idx` only (see `_run`, out_rows)."""
+        F, dev = self.hidden_channels, p.device
+        ns = int(idx.numel())
+        q = self._subplan(p, ns)
+        call("adk_gather_rows", dev, ptr(p.x), ptr(idx), ns, F, ptr(q.x))
+        call("adk_gather_rows", dev, ptr(vec), ptr(idx), ns, 3 * F, ptr(q.vecbuf))
+        presplit = self._update(q, l, q.vecbuf, False)
+        self._heads(q, q.vecbuf, presplit)
+        for k in range(2 if self.so3_denoising else 1):
+            call("adk_scatter_rows", dev, ptr(q.out[k]), ptr(idx), ns, 3, ptr(p.out[k]))
 
     def _refuse_training(self) -> None:
         if torch.is_grad_enabled() and self.training:

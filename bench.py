@@ -287,6 +287,43 @@ def run_ours(args):
     value = world * S_per * args.steps / (ms / 1e3)
     model.check_status(plan)
 
+    # ---- the step exactly as adsorbdiff_b200.Denoiser replays it ---------------------------------------
+    # (weights' operand planes prepared once per run; last message layer, its update block and the heads on the
+    # adsorbate rows only -- the only rows the SE(3) update reads; positions bit-identical, tests/test_gpu_parity.py)
+    flags = (tags == 2).to(torch.int32).contiguous()
+    idx = torch.nonzero(flags).flatten().to(torch.int32).contiguous()
+
+    def sampler_step():
+        model._run(plan, z, pos, weights_ready=True, out_rows=(idx, flags))
+        _cabi.call("adk_se3_step", dev, _cabi.ptr(pos), _cabi.ptr(plan.cell_f32), _cabi.ptr(plan.atom_off),
+                   _cabi.ptr(tags), _cabi.ptr(fixed), _cabi.ptr(plan.out[0]), _cabi.ptr(plan.out[1]),
+                   _cabi.ptr(sched), _cabi.ptr(step), S_per, _cabi.ptr(max_upd))
+
+    step.zero_()
+    l0 = _cabi.launch_count
+    sampler_step()
+    sampler_launches = _cabi.launch_count - l0
+    torch.cuda.synchronize(dev)
+    graph2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph2):
+        sampler_step()
+    for _ in range(max(args.warmup, 3)):
+        graph2.replay()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(args.steps):
+        if i % total_steps == 0:
+            step.zero_()
+        graph2.replay()
+    s1.record()
+    barrier()
+    ts = torch.tensor([s0.elapsed_time(s1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    sampler_ms = float(ts.item())
+    model.check_status(plan)
+
     # ---- e2e: the same steps through the public API with HOST buffers ------------------------------
     # every step: pinned host positions -> device (H2D), `model(batch)` (the reference-facing forward, which
     # also reads the device status word), adk_se3_step through the C ABI, new positions -> pinned host (D2H).
@@ -388,6 +425,11 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (per-step activation working set ~%.1f GB)" % (N * F * 4 * 22 / 1e9),
                    "cuda_graph": True, "early_stop": False},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * 12, "d2h_bytes_per_step": N * 12},
+        "sampler_step": {"value": world * S_per * args.steps / (sampler_ms / 1e3), "unit": UNIT,
+                         "ms_per_step": sampler_ms / args.steps, "launches_per_step": sampler_launches,
+                         "what": "the step as adsorbdiff_b200.Denoiser replays it: last layer + heads on the adsorbate "
+                                 "rows only, weight operand planes prepared once per run; positions identical to the "
+                                 "full forward timed by `value`"},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "clocks": clocks,

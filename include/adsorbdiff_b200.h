@@ -186,8 +186,10 @@ int adk_split_f16_transpose(const float* w, int rows, int cols, float scale, voi
  * source features of one system), or negative ADK_ERANGE if that exceeds the 227 KB of an sm_100a CTA (the
  * caller then uses adk_message for the batch). */
 int64_t adk_message_mma_smem_bytes(int R, int n_max);
-int adk_message_mma(const int32_t* atom_off, int B, int n_max, const int32_t* row_start,
-                    const int32_t* row_deg, const int32_t* e_src, const float* e_geo, const float* xh,
+int adk_message_mma(const int32_t* atom_off, int B, int n_max,
+                    const int32_t* row_sel /* NULL, or [N] flags: only rows with a non-zero flag are computed and
+                                              written (the sampler's last layer: adsorbate rows) */,
+                    const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const float* e_geo, const float* xh,
                     const float* vec_in, const void* wt_split, float w_scale, const float* b_rbf,
                     const float* rbf_offset, int F, int R, float cutoff, int envelope_exponent,
                     float comp, float* x_io, float* vec_out,
@@ -207,6 +209,12 @@ int adk_update_gate(const float* h, const float* dot, const float* vp, const flo
                     int N, int F, float* x, float* vec,
                     void* vec_split /* fp16 [2][split_rows][F] planes of the new vec (row = atom*3+xyz), or NULL */,
                     int64_t split_rows, float split_scale, uint32_t* status, void* stream);
+
+/* Row gather / scatter of fp32 matrices with W columns: dst[i] = src[rows[i]] / dst[rows[i]] = src[i],
+ * i < M.  Used by the sampler, which needs the last layer and the output heads only for the adsorbate atoms
+ * (Denoiser._get_ads_output, denoising_torch.py:460-467, averages the scores over tags == 2 and reads nothing else). */
+int adk_gather_rows(const float* src, const int32_t* rows, int M, int W, float* dst, void* stream);
+int adk_scatter_rows(const float* src, const int32_t* rows, int M, int W, float* dst, void* stream);
 
 /* GatedEquivariantBlock (painn_denoising.py:688-697), the parts around its linears:
  * prep: cat[N][2C] = [x | ||v1p||_xyz] from v1p[N][3][C] = vec1_proj(v);

@@ -403,3 +403,43 @@ def test_symmetry_properties_large_batch(model):
     # NOT tested: permutation of atoms.  The reference is not permutation-equivariant: after the per-atom top-k it
     # keeps the directed edges with source index < target index and mirrors them (painn_denoising.py:262-327), so
     # which of an asymmetric top-k pair survives depends on the atom numbering.
+
+
+def test_selected_rows_tail_is_bit_identical(model):
+    """`_run(out_rows=...)` (the sampler's mode: last message layer, its update block and the heads on the adsorbate
+    rows only) writes exactly the values the full forward writes at those rows."""
+    _reset_sticky_pbc()
+    b = S.make_batch(48, first_id=7).to("cuda:0")
+    full = [t.clone() for t in model(b)]
+    plan, z, pos = model._prepare(b)
+    flags = (b.tags == 2).to(torch.int32).contiguous()
+    idx = torch.nonzero(flags).flatten().to(torch.int32).contiguous()
+    for o in plan.out:
+        o.fill_(float("nan"))
+    model._run(plan, z, pos, out_rows=(idx, flags))
+    torch.cuda.synchronize()
+    model.check_status(plan)
+    sel = idx.long()
+    rest = torch.ones(plan.N, dtype=torch.bool, device="cuda:0")
+    rest[sel] = False
+    for got, ref in zip(plan.out, full):
+        assert torch.equal(got[sel], ref[sel])
+        assert torch.isnan(got[rest]).all()   # nothing else is touched
+
+
+def test_sampler_full_forward_option_gives_the_same_trajectory(golden, sampler_weights):
+    """denoising_pos_params["full_forward"] = True evaluates every atom like the reference; the positions are
+    identical to the default (adsorbate-rows) mode, step by step."""
+    _reset_sticky_pbc()
+    m = PaiNN(None, 0, 1, so3_denoising=True).to("cuda:0").eval()
+    m.load_state_dict(sampler_weights, strict=True)
+    g = golden("sampler")
+    params = ast.literal_eval(str(g["params"]))
+    params["early_stop"] = False
+    runs = []
+    for full in (False, True):
+        b = sampler_batch().to("cuda:0")
+        torch.manual_seed(1234)
+        _, frames = _run_denoiser(m, b, dict(params, full_forward=full), True)
+        runs.append(frames)
+    assert np.array_equal(runs[0], runs[1])
