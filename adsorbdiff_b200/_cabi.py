@@ -32,6 +32,7 @@ SIGNATURES = {
     "adk_set_tc_pair": (c_int, [c_int]),
     "adk_gather_rows": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "adk_scatter_rows": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "adk_mark_sources": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P]),
     "adk_neighbors": (c_int, [_P, _P, _P, c_int, c_int, ctypes.POINTER(c_int32), c_float, c_int,
                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "adk_export_edges": (c_int, [_P, _P, _P, c_int, ctypes.POINTER(c_int32), c_int, _P, _P, _P, _P,
@@ -69,7 +70,7 @@ launch_count = 0  # kernels launched through this binding (bench.py reports it)
 
 _LAUNCHES = {  # kernels behind one entry-point call
     "adk_neighbors": 1, "adk_export_edges": 2, "adk_embed": 1, "adk_layernorm": 1, "adk_linear": 1, "adk_split_f16": 1, "adk_split_f16_multi": 1, "adk_linear_tc": 1,
-    "adk_message": 1, "adk_message_tc": 1, "adk_message_mma": 1, "adk_split_f16_transpose": 1, "adk_update_prep": 1, "adk_update_gate": 1, "adk_head_prep": 1, "adk_head_gate": 1, "adk_gather_rows": 1, "adk_scatter_rows": 1,
+    "adk_message": 1, "adk_message_tc": 1, "adk_message_mma": 1, "adk_split_f16_transpose": 1, "adk_update_prep": 1, "adk_update_gate": 1, "adk_head_prep": 1, "adk_head_gate": 1, "adk_gather_rows": 1, "adk_scatter_rows": 1, "adk_mark_sources": 2,
     "adk_init_placement": 1, "adk_se3_step": 2,
 }
 

@@ -39,7 +39,7 @@ constexpr int MM_SRC_STRIDE = 112;
 
 struct MmParams {
     const int32_t* atom_off;
-    const int32_t* row_sel;     // optional [N] flags: only rows with a non-zero flag are computed and written
+    const int32_t* row_sel;     // optional [N]: 1 = compute the row, 2 = pass vec through (x untouched), 0 = leave untouched
     const int32_t* row_start;
     const int32_t* row_deg;
     const int32_t* e_src;
@@ -154,11 +154,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     // Rows are claimed dynamically, longest first (LPT): with 12 warps and ~82 rows of 3-4 chunks each a fixed
     // round-robin leaves the slowest warp ~5 % behind the mean.  Rank by (degree desc, index asc): a permutation.
     for (int r = threadIdx.x; r < n; r += MM_THREADS) {
-        if (P.row_sel && P.row_sel[a0 + r] == 0) continue;
+        if (P.row_sel && P.row_sel[a0 + r] != 1) continue;
         const int dr = P.row_deg[a0 + r];
         int rank = 0;
         for (int u = 0; u < n; ++u) {
-            if (P.row_sel && P.row_sel[a0 + u] == 0) continue;
+            if (P.row_sel && P.row_sel[a0 + u] != 1) continue;
             const int du = P.row_deg[a0 + u];
             rank += (du > dr || (du == dr && u < r)) ? 1 : 0;
         }
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     }
     if (threadIdx.x < 32) {   // warp 0: number of selected rows, claim counter
         int c = 0;
-        for (int r = threadIdx.x; r < n; r += 32) c += (!P.row_sel || P.row_sel[a0 + r] != 0) ? 1 : 0;
+        for (int r = threadIdx.x; r < n; r += 32) c += (!P.row_sel || P.row_sel[a0 + r] == 1) ? 1 : 0;
         c = __reduce_add_sync(ADK_FULL_MASK, c);
         if (threadIdx.x == 0) { s_next[0] = 0; s_next[1] = c; }
     }
@@ -185,6 +185,27 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     const float sqrt_3 = 1.7320508075688772f;
     const float inv_sqrt_h = 0.57735026918962576451f / sqrtf((float)F);   // includes the 1/sqrt(3) of x_ij2
 
+    // pass-through rows (row_sel == 2): this slice of vec_in is copied to vec_out (+ its operand planes), so that
+    // everything downstream of an unselected row still sees values of the network's own scale
+    if (P.row_sel && blockIdx.z == 0) {
+        for (int r = warp; r < n; r += MM_WARPS) {
+            if (P.row_sel[a0 + r] != 2) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const size_t off = ((size_t)(a0 + r) * 3 + c) * F + f0 + lane;
+                const float v = has_vec ? P.vec_in[off] : 0.f;
+                P.vec_out[off] = v;
+                if (P.vsplit) {
+                    __half h, l;
+                    bool overflow = false;
+                    adk::split_f16x2(v, P.vsplit_scale, h, l, overflow);
+                    P.vsplit[off] = h;
+                    P.vsplit[P.vsplit_plane + off] = l;
+                    if (overflow && P.status) atomicOr(P.status, ADK_STATUS_F16_OVERFLOW);
+                }
+            }
+        }
+    }
     // gridDim.z > 1 (a handful of systems only): the target rows of a system are dealt to several CTAs
     const int n_rows = s_next[1];
     while (true) {

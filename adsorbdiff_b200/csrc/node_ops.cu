@@ -229,6 +229,22 @@ int move_rows(const float* src, const int32_t* rows, int M, int W, float* dst, v
     return 0;
 }
 
+__global__ void fill_i32_kernel(int32_t* __restrict__ out, int N, int32_t v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = v;
+}
+// one warp per selected row: mark the row and the sources of its in-edges (benign races: every writer stores 1)
+__global__ void mark_sources_kernel(const int32_t* __restrict__ row_start, const int32_t* __restrict__ row_deg,
+                                    const int32_t* __restrict__ e_src, const int32_t* __restrict__ sel, int n_sel,
+                                    int32_t* __restrict__ out) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + adk::warp_id();
+    if (w >= n_sel) return;
+    const int t = sel[w];
+    if (adk::lane_id() == 0) out[t] = 1;
+    const int start = row_start[t], deg = row_deg[t];
+    for (int e = adk::lane_id(); e < deg; e += 32) out[e_src[start + e]] = 1;
+}
+
 inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -305,4 +321,15 @@ extern "C" int adk_gather_rows(const float* src, const int32_t* rows, int M, int
 
 extern "C" int adk_scatter_rows(const float* src, const int32_t* rows, int M, int W, float* dst, void* stream) {
     return move_rows<true>(src, rows, M, W, dst, stream);
+}
+
+extern "C" int adk_mark_sources(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
+                                const int32_t* sel, int n_sel, int N, int32_t* out, void* stream) {
+    if (!row_start || !row_deg || !e_src || !sel || !out || n_sel <= 0 || N <= 0) return ADK_EINVAL;
+    cudaStream_t st = adk::as_stream(stream);
+    fill_i32_kernel<<<(N + 255) / 256, 256, 0, st>>>(out, N, 2);
+    ADK_LAUNCH_CHECK();
+    mark_sources_kernel<<<(n_sel + 7) / 8, 256, 0, st>>>(row_start, row_deg, e_src, sel, n_sel, out);
+    ADK_LAUNCH_CHECK();
+    return 0;
 }

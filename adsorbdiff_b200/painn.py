@@ -526,7 +526,16 @@ class PaiNN(nn.Module):
                          ptr(p.status))
                 pruned = out_rows is not None and l == self.num_layers - 1 and trace is None
                 planes = self._tc_ok(u.vec_proj) and not pruned
-                call("adk_message_mma", dev, ptr(p.atom_off), p.B, p.n_max, ptr(out_rows[1]) if pruned else None,
+                row_sel = out_rows[1] if pruned else None
+                if out_rows is not None and trace is None and l == self.num_layers - 2:
+                    # the last layer is evaluated at out_rows only, so THIS layer's messages are needed only at those
+                    # rows and at the sources of their in-edges; every other row passes vec through unchanged
+                    if getattr(p, "sel2", None) is None:
+                        p.sel2 = torch.empty(N, dtype=torch.int32, device=dev)
+                    call("adk_mark_sources", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(out_rows[0]),
+                         int(out_rows[0].numel()), N, ptr(p.sel2))
+                    row_sel = p.sel2
+                call("adk_message_mma", dev, ptr(p.atom_off), p.B, p.n_max, ptr(row_sel) if row_sel is not None else None,
                      ptr(p.row_start), ptr(p.row_deg),
                      ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wt),
                      self.W_SCALE, ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R,

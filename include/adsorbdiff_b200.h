@@ -187,8 +187,8 @@ int adk_split_f16_transpose(const float* w, int rows, int cols, float scale, voi
  * caller then uses adk_message for the batch). */
 int64_t adk_message_mma_smem_bytes(int R, int n_max);
 int adk_message_mma(const int32_t* atom_off, int B, int n_max,
-                    const int32_t* row_sel /* NULL, or [N] flags: only rows with a non-zero flag are computed and
-                                              written (the sampler's last layer: adsorbate rows) */,
+                    const int32_t* row_sel /* NULL, or [N]: 1 = compute the row, 2 = pass it through (vec_out =
+                                              vec_in, x untouched), 0 = leave it untouched (the sampler's tail) */,
                     const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const float* e_geo, const float* xh,
                     const float* vec_in, const void* wt_split, float w_scale, const float* b_rbf,
                     const float* rbf_offset, int F, int R, float cutoff, int envelope_exponent,
@@ -214,6 +214,10 @@ int adk_update_gate(const float* h, const float* dot, const float* vp, const flo
  * i < M.  Used by the sampler, which needs the last layer and the output heads only for the adsorbate atoms
  * (Denoiser._get_ads_output, denoising_torch.py:460-467, averages the scores over tags == 2 and reads nothing else). */
 int adk_gather_rows(const float* src, const int32_t* rows, int M, int W, float* dst, void* stream);
+/* Rows a message layer has to compute so that the NEXT layer can be evaluated at the rows `sel` only: out[i] = 1 for
+ * i in sel and for every source of an in-edge of a row in sel, else 2 (the row_sel codes of adk_message_mma). */
+int adk_mark_sources(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const int32_t* sel,
+                     int n_sel, int N, int32_t* out, void* stream);
 int adk_scatter_rows(const float* src, const int32_t* rows, int M, int W, float* dst, void* stream);
 
 /* GatedEquivariantBlock (painn_denoising.py:688-697), the parts around its linears:
