@@ -50,6 +50,7 @@ struct MmParams {
     const float* b_rbf;
     const float* rbf_offset;
     int F, R, n_max;
+    int B, sys_per_cta;   // a CTA walks sys_per_cta consecutive systems (weights staged once)
     float inv_cutoff, coeff, env_a, env_b, env_c;
     int env_p;
     float acc_scale, coeff_sqrt;
@@ -114,8 +115,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     float* s_vec = s_xh + (size_t)P.n_max * MM_SRC_STRIDE;           // [n][MM_SRC_STRIDE]
     int16_t* s_order = reinterpret_cast<int16_t*>(s_vec + (size_t)P.n_max * MM_SRC_STRIDE);   // rows, longest first
     int* s_next = reinterpret_cast<int*>(s_order + ((P.n_max + 7) & ~7));                   // next unclaimed position
-    const int b = blockIdx.x, f0 = blockIdx.y * MM_SF;
-    const int a0 = P.atom_off[b], n = P.atom_off[b + 1] - a0;
+    const int f0 = blockIdx.y * MM_SF;
     const int lane = adk::lane_id(), warp = adk::warp_id();
     const bool has_vec = P.vec_in != nullptr;
 
@@ -134,6 +134,9 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
         const int g = threadIdx.x >> 5, f = threadIdx.x & 31;
         s_bias[g * 32 + (f >> 4) * 16 + ((f >> 1) & 3) * 4 + ((f >> 3) & 1) * 2 + (f & 1)] = P.b_rbf[g * F + f0 + f];
     }
+    const int b_first = blockIdx.x * P.sys_per_cta, b_end = min(P.B, b_first + P.sys_per_cta);
+    for (int b = b_first; b < b_end; ++b) {
+    const int a0 = P.atom_off[b], n = P.atom_off[b + 1] - a0;
     // ---- stage the system's source features: one 128-byte segment per (atom, group) per warp ----
     {
         // feature f = nt * 8 + 2 * qt + h of the slice lands at [g][qt][nt][h]
@@ -500,6 +503,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
             }
         }
     }
+    __syncthreads();   // every warp is done with this system's staged sources before the next system overwrites them
+    }
 }
 
 // w[rows][cols] fp32 -> fp16x2 planes of the TRANSPOSE: dst[2][cols][rows]
@@ -573,11 +578,16 @@ extern "C" int adk_message_mma(const int32_t* atom_off, int B, int n_max, const 
     P.x_io = x_io; P.vec_out = vec_out;
     P.vsplit = reinterpret_cast<__half*>(vec_split); P.vsplit_plane = split_rows * (int64_t)F;
     P.vsplit_scale = split_scale; P.status = status;
+    // When only a few rows per system are selected (the sampler's last layer: the adsorbate atoms), staging the weight
+    // slice dominates a CTA: let one CTA walk several systems and stage the weights once.
+    P.B = B;
+    P.sys_per_cta = 1;
+    if (row_sel && B >= 148) P.sys_per_cta = 4;
     // one CTA per (system, feature slice) fills the GPU from ~10 systems on; below that split the rows as well,
     // as long as all CTAs are resident at once (one per SM)
     int row_splits = 1;
     while (row_splits < 8 && (long long)B * (F / MM_SF) * row_splits * 2 <= 148) row_splits *= 2;
-    message_mma_kernel<<<dim3(B, F / MM_SF, row_splits), MM_THREADS, smem, adk::as_stream(stream)>>>(P);
+    message_mma_kernel<<<dim3((B + P.sys_per_cta - 1) / P.sys_per_cta, F / MM_SF, row_splits), MM_THREADS, smem, adk::as_stream(stream)>>>(P);
     ADK_LAUNCH_CHECK();
     return 0;
 }

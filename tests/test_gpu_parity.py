@@ -405,11 +405,13 @@ def test_symmetry_properties_large_batch(model):
     # which of an asymmetric top-k pair survives depends on the atom numbering.
 
 
-def test_selected_rows_tail_is_bit_identical(model):
+@pytest.mark.parametrize("systems", [3, 48, 150])   # 150: a CTA of the row-selected message kernel walks 4 systems
+def test_selected_rows_tail_is_bit_identical(model, systems):
     """`_run(out_rows=...)` (the sampler's mode: last message layer, its update block and the heads on the adsorbate
-    rows only) writes exactly the values the full forward writes at those rows."""
+    rows only, the layer before it on those rows and their sources) writes exactly the values the full forward
+    writes at those rows."""
     _reset_sticky_pbc()
-    b = S.make_batch(48, first_id=7).to("cuda:0")
+    b = S.make_batch(systems, first_id=7).to("cuda:0")
     full = [t.clone() for t in model(b)]
     plan, z, pos = model._prepare(b)
     flags = (b.tags == 2).to(torch.int32).contiguous()
