@@ -14,10 +14,12 @@ import torch
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libadsorbdiff_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+SCHED_COLS = 6
 STATUS_EMPTY_SYSTEM = 1
 STATUS_ROW_OVERFLOW = 2
 STATUS_F16_OVERFLOW = 4
+STATUS_BAD_ELEMENT = 8
 MAX_IMAGES = 2048
 MAX_ATOMS_PER_SYSTEM = 1024
 ACT_NONE, ACT_SSILU = 0, 1
@@ -37,7 +39,7 @@ SIGNATURES = {
                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "adk_export_edges": (c_int, [_P, _P, _P, c_int, ctypes.POINTER(c_int32), c_int, _P, _P, _P, _P,
                                  _P, c_int64, _P, _P, _P, _P, _P]),
-    "adk_embed": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "adk_embed": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "adk_layernorm": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P, c_int64, c_float, _P, _P]),
     "adk_linear": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int, c_int, _P, c_int64, _P]),
     "adk_split_f16": (c_int, [_P, c_int64, c_int, c_int, c_float, _P, c_int64, _P, _P]),
@@ -56,7 +58,8 @@ SIGNATURES = {
     "adk_head_prep": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int64, c_float, _P, _P]),
     "adk_head_gate": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int64, c_float, _P, _P]),
     "adk_init_placement": (c_int, [_P, _P, _P, _P, _P, c_int, _P]),
-    "adk_se3_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
+    "adk_se3_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P]),
+    "adk_early_stop": (c_int, [_P, c_int, c_float, _P, _P, _P, _P, c_int64, _P]),
 }
 
 
@@ -71,7 +74,7 @@ launch_count = 0  # kernels launched through this binding (bench.py reports it)
 _LAUNCHES = {  # kernels behind one entry-point call
     "adk_neighbors": 1, "adk_export_edges": 2, "adk_embed": 1, "adk_layernorm": 1, "adk_linear": 1, "adk_split_f16": 1, "adk_split_f16_multi": 1, "adk_linear_tc": 1,
     "adk_message": 1, "adk_message_tc": 1, "adk_message_mma": 1, "adk_split_f16_transpose": 1, "adk_update_prep": 1, "adk_update_gate": 1, "adk_head_prep": 1, "adk_head_gate": 1, "adk_gather_rows": 1, "adk_scatter_rows": 1, "adk_mark_sources": 2,
-    "adk_init_placement": 1, "adk_se3_step": 2,
+    "adk_init_placement": 1, "adk_se3_step": 2, "adk_early_stop": 2,
 }
 
 
@@ -120,9 +123,15 @@ def ptr(t: torch.Tensor | None):
 
 
 def call(name: str, device: torch.device, *args) -> None:
-    """Invoke an entry point on torch's current stream of `device`; raise on a non-zero code."""
+    """Invoke an entry point on torch's current stream of `device`; raise on a non-zero code.
+    The launch happens with `device` current (kernels and streams belong to a device), whatever the caller's
+    current device is."""
     global launch_count
     _ensure_init(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        with torch.cuda.device(idx):
+            return call(name, torch.device("cuda", idx), *args)
     stream = torch.cuda.current_stream(device).cuda_stream
     rc = getattr(load(), name)(*args, stream)
     if rc != 0:

@@ -356,7 +356,11 @@ __global__ void __launch_bounds__(NB_WARPS_MAX * 32) neighbors_kernel(NbParams P
     const int edge_base = 2 * k * a0;
     for (int t = tid; t < n; t += NB_THREADS) {
         P.row_start[a0 + t] = edge_base + s_row_start[t];
-        P.row_deg[a0 + t] = s_kept_cnt[t] + s_rev_cnt[t];
+        // a row beyond the compiled capacity is skipped below (status bit): publish it as EMPTY so that the message
+        // kernels of the same forward / graph replay, which run before the host reads the status word, never walk
+        // its unwritten slots
+        const int deg_t = s_kept_cnt[t] + s_rev_cnt[t];
+        P.row_deg[a0 + t] = deg_t > ADK_MAX_ROW_DEGREE ? 0 : deg_t;
         P.kept_cnt[a0 + t] = s_kept_cnt[t];
     }
     for (int t = tid; t < n * k; t += NB_THREADS) {

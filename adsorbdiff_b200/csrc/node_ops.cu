@@ -8,14 +8,18 @@
 namespace {
 
 __global__ void embed_kernel(const int64_t* __restrict__ z, const float* __restrict__ emb, int num_elements,
-                             int N, int F, float* __restrict__ x, float* __restrict__ vec) {
+                             int N, int F, float* __restrict__ x, float* __restrict__ vec, uint32_t* status) {
     // one float4 per thread over x[N][F]; the same thread clears the 3 vec rows
     const int F4 = F >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)N * F4) return;
     const int nidx = (int)(idx / F4), f4 = (int)(idx - (int64_t)nidx * F4);
     int e = (int)z[nidx] - 1;  // AtomEmbedding: embeddings(Z - 1)
-    e = min(max(e, 0), num_elements - 1);
+    if (e < 0 || e >= num_elements) {
+        // nn.Embedding fails hard on such an index; here: status bit (raised by the host), row clamped meanwhile
+        if (status && f4 == 0) atomicOr(status, ADK_STATUS_BAD_ELEMENT);
+        e = min(max(e, 0), num_elements - 1);
+    }
     reinterpret_cast<float4*>(x)[idx] = reinterpret_cast<const float4*>(emb)[(int64_t)e * F4 + f4];
     if (vec) {
         float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -250,10 +254,10 @@ inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t
 }  // namespace
 
 extern "C" int adk_embed(const int64_t* z, const float* emb, int num_elements, int N, int F, float* x,
-                         float* vec, void* stream) {
+                         float* vec, uint32_t* status, void* stream) {
     if (!z || !emb || !x || N <= 0 || F <= 0 || (F & 3)) return ADK_EINVAL;
     embed_kernel<<<blocks_for((int64_t)N * (F >> 2), 256), 256, 0, adk::as_stream(stream)>>>(z, emb, num_elements,
-                                                                                          N, F, x, vec);
+                                                                                          N, F, x, vec, status);
     ADK_LAUNCH_CHECK();
     return 0;
 }

@@ -92,11 +92,14 @@ __global__ void se3_step_kernel(float* pos, const float* __restrict__ cell, cons
                                 const int32_t* __restrict__ tags, const int32_t* __restrict__ fixed,
                                 const float* __restrict__ score_tr, const float* __restrict__ score_rot,
                                 const float* __restrict__ sched, const int32_t* __restrict__ step, int B,
-                                float* max_abs_upd) {
+                                const float* __restrict__ noise, float* max_abs_upd,
+                                const int32_t* __restrict__ stop) {
     const int b = blockIdx.x * (blockDim.x >> 5) + adk::warp_id();
     if (b >= B) return;
+    if (stop && stop[1]) return;  // the run has stopped early (adk_early_stop): positions stay as they are
     const int s_idx = *step;
-    const float c_tr = sched[3 * s_idx], dt = sched[3 * s_idx + 1], rot_g2 = sched[3 * s_idx + 2];
+    const float* sc = sched + ADK_SCHED_COLS * (size_t)s_idx;
+    const float c_tr = sc[0], dt = sc[1], rot_g2 = sc[2];
     const int lane = adk::lane_id();
     const int a0 = atom_off[b], n = atom_off[b + 1] - a0;
     const float* cl = cell + 9 * (size_t)b;
@@ -105,9 +108,22 @@ __global__ void se3_step_kernel(float* pos, const float* __restrict__ cell, cons
     Mean3 rt = ads_mean(score_rot, tags, fixed, a0, n, lane);  // positions_free[fixed == 1] = 0
     Mean3 com = ads_mean(pos, tags, nullptr, a0, n, lane);
 
-    // ODE step: d_com = 0.5 g^2 dt * score ; rot_vec = ((0.5 * score) * dt) * g_rot^2
+    // ODE step (:269-272): d_com = 0.5 g^2 dt * score ; rot_vec = ((0.5 * score) * dt) * g_rot^2
     float upd[3] = {c_tr * tr.x, c_tr * tr.y, 0.f};  // z component zeroed (:297)
     float rv[3] = {((0.5f * rt.x) * dt) * rot_g2, ((0.5f * rt.y) * dt) * rot_g2, ((0.5f * rt.z) * dt) * rot_g2};
+    if (noise) {
+        // SDE step (:273-295): d_com = (g^2 dt) * score + (g sqrt(dt)) * z_tr ;
+        // rot_vec = (score * dt) * g_rot^2 + (g_rot sqrt(dt)) * z_rot, every product and the sum rounded to fp32
+        // like the reference's tensor expression.  noise[step][2][B][3] holds this step's two normal draws.
+        const float c_sde = sc[3], n_tr = sc[4], n_rot = sc[5];
+        const float* zt = noise + ((size_t)s_idx * 2 * B + b) * 3;
+        const float* zr = zt + (size_t)B * 3;
+        upd[0] = __fadd_rn(__fmul_rn(c_sde, tr.x), __fmul_rn(n_tr, zt[0]));
+        upd[1] = __fadd_rn(__fmul_rn(c_sde, tr.y), __fmul_rn(n_tr, zt[1]));
+        rv[0] = __fadd_rn(__fmul_rn(__fmul_rn(rt.x, dt), rot_g2), __fmul_rn(n_rot, zr[0]));
+        rv[1] = __fadd_rn(__fmul_rn(__fmul_rn(rt.y, dt), rot_g2), __fmul_rn(n_rot, zr[1]));
+        rv[2] = __fadd_rn(__fmul_rn(__fmul_rn(rt.z, dt), rot_g2), __fmul_rn(n_rot, zr[2]));
+    }
 
     // wrap the centre of mass into the cell: f = solve(cell, com + upd); f %= 1 (twice); back (:298-310)
     float target[3] = {com.x + upd[0], com.y + upd[1], com.z + upd[2]};
@@ -144,7 +160,37 @@ __global__ void se3_step_kernel(float* pos, const float* __restrict__ cell, cons
     }
 }
 
-__global__ void bump_step_kernel(int32_t* step) { *step += 1; }
+__global__ void bump_step_kernel(int32_t* step, const int32_t* stop) {
+    if (!stop || !stop[1]) *step += 1;
+}
+
+// The reference's batch-wide convergence test (denoising_torch.py:312-320): allclose(delta COM, 0, rtol 1e-3,
+// atol 1e-3) over ALL systems bumps a counter; at the tenth hit the loop breaks BEFORE that step's update is
+// applied.  stop[0] = hit count, stop[1] = stopped flag, stop[2] = number of steps applied when it stopped.
+__global__ void early_stop_decide_kernel(const float* __restrict__ max_abs_upd, int B, float atol,
+                                         const int32_t* __restrict__ step, int32_t* stop) {
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    if (stop[1]) return;
+    int bad = 0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) bad |= !(max_abs_upd[i] <= atol) ? 1 : 0;
+    if (bad) s_any = 1;
+    __syncthreads();
+    if (threadIdx.x == 0 && !s_any) {
+        stop[0] += 1;
+        if (stop[0] == 10) {
+            stop[1] = 1;
+            stop[2] = *step - 1;  // adk_se3_step already bumped the counter for this step
+        }
+    }
+}
+__global__ void early_stop_rollback_kernel(float* pos, const float* __restrict__ prev, int64_t n,
+                                           const int32_t* __restrict__ stop) {
+    if (!stop[1]) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        pos[i] = prev[i];
+}
 
 }  // namespace
 
@@ -158,13 +204,25 @@ extern "C" int adk_init_placement(float* pos, const float* cell, const int32_t* 
 
 extern "C" int adk_se3_step(float* pos, const float* cell, const int32_t* atom_off, const int32_t* tags,
                             const int32_t* fixed, const float* score_tr, const float* score_rot,
-                            const float* sched, int32_t* step, int B, float* max_abs_upd, void* stream) {
+                            const float* sched, int32_t* step, int B, const float* noise, float* max_abs_upd,
+                            const int32_t* stop, void* stream) {
     if (!pos || !cell || !atom_off || !tags || !fixed || !score_tr || !score_rot || !sched || !step || B <= 0)
         return ADK_EINVAL;
     se3_step_kernel<<<(B + 3) / 4, 128, 0, adk::as_stream(stream)>>>(pos, cell, atom_off, tags, fixed, score_tr,
-                                                                   score_rot, sched, step, B, max_abs_upd);
+                                                                   score_rot, sched, step, B, noise, max_abs_upd, stop);
     ADK_LAUNCH_CHECK();
-    bump_step_kernel<<<1, 1, 0, adk::as_stream(stream)>>>(step);
+    bump_step_kernel<<<1, 1, 0, adk::as_stream(stream)>>>(step, stop);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int adk_early_stop(const float* max_abs_upd, int B, float atol, const int32_t* step, int32_t* stop,
+                              float* pos, const float* prev, int64_t n_values, void* stream) {
+    if (!max_abs_upd || !step || !stop || !pos || !prev || B <= 0 || n_values <= 0) return ADK_EINVAL;
+    early_stop_decide_kernel<<<1, 256, 0, adk::as_stream(stream)>>>(max_abs_upd, B, atol, step, stop);
+    ADK_LAUNCH_CHECK();
+    const int blocks = (int)((n_values + 255) / 256 < 1184 ? (n_values + 255) / 256 : 1184);
+    early_stop_rollback_kernel<<<blocks, 256, 0, adk::as_stream(stream)>>>(pos, prev, n_values, stop);
     ADK_LAUNCH_CHECK();
     return 0;
 }

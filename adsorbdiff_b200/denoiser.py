@@ -13,9 +13,10 @@ in a device schedule table indexed by a device step counter, so replays need no 
 Deviations from the reference, all opt-in or documented in DESIGN.md:
   * the EMA weight swap of `predict_denoising` (3 full-model copies per step,
     sde_denoising_trainer.py:580-583, 650-651) is hoisted out of the loop (once per run);
-  * the reference checks `allclose(delta_com, 0)` on the host every step (:312-320); here the
-    check is every `early_stop_every` steps (default 1 = identical), or never when
-    `denoising_pos_params["early_stop"]` is False (benchmark setting);
+  * the reference checks `allclose(delta_com, 0)` on the host every step (:312-320); here the same
+    test runs on the device after every step (`adk_early_stop`: counter, break before the tenth hit is
+    applied) and the host only polls the result every `early_stop_every` steps (default 10) -- final
+    positions and step count are the reference's; `denoising_pos_params["early_stop"] = False` disables it;
   * per-step ASE trajectory writing (:358-367) needs ASE, which is optional here: frames are
     collected on the device and written once at the end (`.traj` through ASE when importable,
     else `<sid>.npz`).
@@ -60,8 +61,9 @@ class DiffTorchCalc:
 
 
 def schedule_table(params: dict, device) -> torch.Tensor:
-    """[num_steps][3] = (0.5*tr_g^2*dt, dt, fp32(rot_g^2)) evaluated with the reference's own torch/numpy
-    expressions and dtypes (denoising_torch.py:209-261): tr_g is fp32, rot_g is float64."""
+    """[num_steps][ADK_SCHED_COLS] per-step scalars evaluated with the reference's own torch/numpy expressions and
+    dtypes (denoising_torch.py:209-261, 269-295): tr_g is fp32, rot_g is float64.
+    Columns: 0.5*tr_g^2*dt | dt | fp32(rot_g^2) | tr_g^2*dt | tr_g*sqrt(dt) | fp32(rot_g*sqrt(dt))."""
     num_steps = params["num_steps"]
     lo, hi = params["ads_std_low"], params["ads_std_high"]
     rlo, rhi = params["rot_std_low"], params["rot_std_high"]
@@ -74,9 +76,25 @@ def schedule_table(params: dict, device) -> torch.Tensor:
         tr_g = tr_sigma * (2 * np.log(hi / lo)) ** 0.5
         rot_g = 2 * rot_sigma * torch.sqrt(torch.tensor(np.log(rhi / rlo)))
         dt = tr_schedule[t_idx] - tr_schedule[t_idx + 1] if t_idx < num_steps - 1 else tr_schedule[t_idx]
-        c_tr = 0.5 * tr_g**2 * dt
-        rows.append([float(c_tr), float(dt), float((rot_g**2).to(torch.float32))])
-    return torch.tensor(rows, dtype=torch.float32, device=device)
+        sqrt_dt = torch.sqrt(dt)  # what np.sqrt(dt) evaluates to for a 0-dim fp32 tensor
+        rows.append([float(0.5 * tr_g**2 * dt), float(dt), float((rot_g**2).to(torch.float32)),
+                     float(tr_g**2 * dt), float(tr_g * sqrt_dt), float((rot_g * sqrt_dt).to(torch.float32))])
+    out = torch.tensor(rows, dtype=torch.float32, device=device)
+    assert out.shape[1] == _cabi.SCHED_COLS
+    return out
+
+
+def draw_sde_noise(num_steps: int, num_systems: int, device) -> torch.Tensor:
+    """[num_steps][2][B][3]: the standard-normal draws of the SDE branch, made with the reference's calls in the
+    reference's order (tr_z then rot_z every step, `torch.normal(mean=0, std=1, size=[B,3], device=device)`,
+    denoising_torch.py:274-289) so that the same generator state gives the same trajectory.  They are drawn up
+    front because the step runs as a CUDA-graph replay; an early-stopped run therefore advances the generator
+    further than the reference would."""
+    out = torch.empty(num_steps, 2, num_systems, 3, dtype=torch.float32, device=device)
+    for t in range(num_steps):
+        out[t, 0] = torch.normal(mean=0, std=1, size=(num_systems, 3), device=device)
+        out[t, 1] = torch.normal(mean=0, std=1, size=(num_systems, 3), device=device)
+    return out
 
 
 class Denoiser:
@@ -92,7 +110,15 @@ class Denoiser:
         early_stop_batch: bool = False,
         logger=None,
         use_cuda_graph: bool = True,
+        init_noise: Optional[torch.Tensor] = None,
+        sde_noise: Optional[torch.Tensor] = None,
     ) -> None:
+        """Same arguments as the reference `Denoiser` (denoising_torch.py:18-62) plus:
+        `init_noise` [B,3]: the uniform draws of the initial placement (:215) when the caller has made them --
+        a rank that holds rows [a, b) of a larger job passes rows [a, b) of the job-wide `torch.rand(B_total, 3)`
+        (`partition.initial_noise`), so that an N-rank run reproduces the 1-rank run; default: drawn here from the
+        CPU global generator exactly like the reference.
+        `sde_noise` [num_steps,2,B,3]: the normal draws of the SDE branch (`draw_sde_noise`), same idea."""
         self.batch = batch
         self.model = model  # DiffTorchCalc(trainer) like the reference, or a PaiNN directly
         self.device = device
@@ -102,6 +128,8 @@ class Denoiser:
         self.early_stop_batch = early_stop_batch
         self.denoising_pos_params = denoising_pos_params
         self.use_cuda_graph = use_cuda_graph
+        self.init_noise = init_noise
+        self.sde_noise = sde_noise
         trainer = getattr(model, "model", model)
         self.trainer = trainer if hasattr(trainer, "predict_denoising") else None
         self.net = unwrap_model(trainer)
@@ -126,16 +154,18 @@ class Denoiser:
         params = self.denoising_pos_params
         if "ads_std_low" not in params:
             return
-        if not params.get("ode", True):
-            raise NotImplementedError("only the ODE sampler (the reference default, ode=True) is built")
+        ode = bool(params.get("ode", True))
         batch, net = self.batch, self.net
         dev = batch.pos.device
         if dev.type != "cuda":
             raise _cabi.AdkError("Denoiser needs the batch on a CUDA device (no CPU fallback)")
         num_steps = params["num_steps"]
         early_stop = params.get("early_stop", True)
-        check_every = int(params.get("early_stop_every", 1))
-        record = bool(self.traj_dir)
+        # the stop decision is taken on the device after every step (adk_early_stop: exact reference semantics);
+        # the host only polls the flag, every `early_stop_every` steps, to leave the loop
+        poll_every = max(1, int(params.get("early_stop_every", 10)))
+        status_every = max(1, int(params.get("status_every", 25)))
+        record = bool(self.traj_dir) or bool(params.get("keep_frames", False))
 
         ema = getattr(self.trainer, "ema", None) if self.trainer is not None else None
         if ema:
@@ -150,13 +180,23 @@ class Denoiser:
             fixed = batch.fixed.to(torch.int32).contiguous()
             B = plan.B
             # initial placement: the reference draws on the CPU global generator (:215)
-            noise = torch.rand(B, 3).to(dev)
+            noise = self.init_noise if self.init_noise is not None else torch.rand(B, 3)
+            if tuple(noise.shape) != (B, 3):
+                raise ValueError(f"init_noise must be [{B}, 3], got {tuple(noise.shape)}")
+            noise = noise.to(dev, torch.float32).contiguous()
             call("adk_init_placement", dev, ptr(pos), ptr(plan.cell_f32), ptr(plan.atom_off), ptr(tags),
                  ptr(noise), B)
             sched = schedule_table(params, dev)
+            sde = None
+            if not ode:
+                sde = self.sde_noise if self.sde_noise is not None else draw_sde_noise(num_steps, B, dev)
+                if tuple(sde.shape) != (num_steps, 2, B, 3):
+                    raise ValueError(f"sde_noise must be [{num_steps}, 2, {B}, 3], got {tuple(sde.shape)}")
+                sde = sde.to(dev, torch.float32).contiguous()
             step = torch.zeros(1, dtype=torch.int32, device=dev)
             max_upd = torch.zeros(B, dtype=torch.float32, device=dev)
             prev = torch.empty_like(pos) if early_stop else None
+            stop = torch.zeros(4, dtype=torch.int32, device=dev) if early_stop else None
             if record:
                 self.frames = torch.empty(num_steps, plan.N, 3, dtype=torch.float32, device=dev)
 
@@ -172,16 +212,19 @@ class Denoiser:
                     out_rows = (idx, flags)
 
             def one_step(weights_ready=False):
-                net._run(plan, z, pos, weights_ready=weights_ready, out_rows=out_rows)
-                call("adk_se3_step", dev, ptr(pos), ptr(plan.cell_f32), ptr(plan.atom_off), ptr(tags), ptr(fixed),
-                     ptr(plan.out[0]), ptr(plan.out[1]), ptr(sched), ptr(step), B, ptr(max_upd))
-
-            graph = None
-            cvg_count = 0
-            t_idx = 0
-            while t_idx < num_steps:
                 if early_stop:
                     prev.copy_(pos)
+                net._run(plan, z, pos, weights_ready=weights_ready, out_rows=out_rows)
+                call("adk_se3_step", dev, ptr(pos), ptr(plan.cell_f32), ptr(plan.atom_off), ptr(tags), ptr(fixed),
+                     ptr(plan.out[0]), ptr(plan.out[1]), ptr(sched), ptr(step), B, ptr(sde), ptr(max_upd), ptr(stop))
+                if early_stop:
+                    call("adk_early_stop", dev, ptr(max_upd), B, 1e-3, ptr(step), ptr(stop), ptr(pos), ptr(prev),
+                         pos.numel())
+
+            graph = None
+            t_idx = 0
+            stopped = False
+            while t_idx < num_steps:
                 if graph is not None:
                     graph.replay()
                 else:
@@ -190,26 +233,26 @@ class Denoiser:
                         torch.cuda.synchronize(dev)
                         net.check_status(plan)
                         graph = torch.cuda.CUDAGraph()
-                        saved_pos, saved_step = pos.clone(), step.clone()
                         # Between the EMA swap-in above and the swap-out below nobody else writes the parameters,
                         # and the eager step just produced their fp16x2 planes: the replayed step does not redo it.
+                        # (capture does not execute: pos / step / stop keep their values)
                         with torch.cuda.graph(graph):
                             one_step(weights_ready=True)
-                        # capture does not execute, but be explicit about state
-                        pos.copy_(saved_pos)
-                        step.copy_(saved_step)
                 t_idx += 1
-                if early_stop and (t_idx % check_every == 0):
-                    # torch.allclose(delta, 0, rtol=1e-3, atol=1e-3) over the whole batch (:312-320)
-                    if bool((max_upd <= 1e-3).all().item()):
-                        cvg_count += 1
-                        if cvg_count == 10:
-                            pos.copy_(prev)  # the reference breaks before applying this step
-                            t_idx -= 1
-                            break
                 if record:
                     self.frames[t_idx - 1].copy_(pos)
+                # a data-dependent failure (a system without neighbours, an operand leaving the fp16 range) is caught
+                # after the first replayed step and then every `status_every` steps, not only at the end of the run
+                if t_idx == 2 or t_idx % status_every == 0:
+                    net.check_status(plan)
+                if early_stop and (t_idx % poll_every == 0 or t_idx == num_steps):
+                    st = stop.tolist()
+                    if st[1]:
+                        t_idx = st[2]  # steps applied before the break (:312-320)
+                        stopped = True
+                        break
             self.steps_run = t_idx
+            self.stopped_early = stopped
             net.check_status(plan)
         finally:
             if ema:
@@ -255,10 +298,23 @@ class Denoiser:
             start += n
 
 
+def _collate(data_list, like):
+    """Re-collate a list of single systems (or finished batches) the way the reference does with
+    `data_list_collater` / `Batch.from_data_list` (ml_relaxation.py:163-167): PyG when the batch is a PyG batch,
+    else the batch class's own `from_data_list` (adsorbdiff_b200.synthetic.SystemBatch has one)."""
+    cls = type(like)
+    if hasattr(cls, "from_data_list") and not cls.__module__.startswith("torch_geometric"):
+        return cls.from_data_list(data_list)
+    from torch_geometric.data import Batch
+
+    return Batch.from_data_list(data_list)
+
+
 def ml_diffuse(batch, model, denoising_pos_params: dict, traj_dir, save_full_traj, device: str = "cuda:0",
                transform=None, early_stop_batch: bool = False, logger=None):
-    """reference: adsorbdiff/relaxation/ml_relaxation.py:98-168 (OOM -> split the batch in two and retry).
-    The re-collation of split batches needs PyG (`to_data_list`); without it the error is re-raised."""
+    """reference: adsorbdiff/relaxation/ml_relaxation.py:98-168.  Like the reference, ANY RuntimeError of a batch
+    (out of memory first of all) frees the cache, splits the batch in two and retries (second half first, :163-165);
+    a single-system batch re-raises."""
     batches = deque([batch])
     done = []
     while batches:
@@ -267,23 +323,24 @@ def ml_diffuse(batch, model, denoising_pos_params: dict, traj_dir, save_full_tra
         den = Denoiser(b, calc, denoising_pos_params, device=device, save_full_traj=save_full_traj,
                        traj_dir=Path(traj_dir) if traj_dir is not None else None, traj_names=b.sid,
                        early_stop_batch=early_stop_batch, logger=logger)
+        e: Optional[RuntimeError] = None
         try:
             done.append(den.run())
-            continue
-        except torch.cuda.OutOfMemoryError as err:
+        except RuntimeError as err:
             e = err
-            torch.cuda.empty_cache()
-        if not hasattr(b, "to_data_list") or len(b.sid) == 1:
-            raise e
-        data_list = b.to_data_list()
-        logging.info(f"Failed to relax batch with size: {len(data_list)}, splitting into two...")
-        from torch_geometric.data import Batch
-
-        mid = len(data_list) // 2
-        batches.appendleft(Batch.from_data_list(data_list[:mid]))
-        batches.appendleft(Batch.from_data_list(data_list[mid:]))
+            if torch.cuda.is_available():
+                torch.cuda.empty_cache()
+        if e is not None:
+            # recovery outside the except clause so that the failed attempt's tensors can be freed (:156-157)
+            if not hasattr(b, "to_data_list"):
+                raise e
+            data_list = b.to_data_list()
+            if len(data_list) == 1:
+                raise e
+            logging.info(f"Failed to relax batch with size: {len(data_list)}, splitting into two...")
+            mid = len(data_list) // 2
+            batches.appendleft(_collate(data_list[:mid], b))
+            batches.appendleft(_collate(data_list[mid:], b))
     if len(done) == 1:
         return done[0]
-    from torch_geometric.data import Batch
-
-    return Batch.from_data_list(done)
+    return _collate(done, batch)

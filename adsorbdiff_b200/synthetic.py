@@ -62,6 +62,40 @@ class SystemBatch:
     def num_graphs(self):
         return int(self.natoms.shape[0])
 
+    _PER_ATOM = ("pos", "atomic_numbers", "tags", "fixed", "force")
+    _PER_SYSTEM = ("cell", "natoms", "y", "pbc")
+
+    def to_data_list(self):
+        """Single-system batches, like PyG's `Batch.to_data_list` (used by ml_diffuse's split-and-retry)."""
+        nat = [int(n) for n in self.natoms.tolist()]
+        off = [0]
+        for n in nat:
+            off.append(off[-1] + n)
+        out = []
+        for i, n in enumerate(nat):
+            f = {}
+            for k, v in self.__dict__.items():
+                if not isinstance(v, torch.Tensor):
+                    continue
+                if k in self._PER_ATOM and v.shape[0] == off[-1]:
+                    f[k] = v[off[i]:off[i + 1]].clone()
+                elif k in self._PER_SYSTEM and v.shape[0] == len(nat):
+                    f[k] = v[i:i + 1].clone()
+            f["batch"] = torch.zeros(n, dtype=torch.long, device=self.pos.device)
+            f["sid"] = [self.sid[i]]
+            out.append(SystemBatch(**f))
+        return out
+
+    @classmethod
+    def from_data_list(cls, data_list):
+        """Concatenate batches (single systems or finished multi-system batches) in order."""
+        keys = [k for k, v in data_list[0].__dict__.items() if isinstance(v, torch.Tensor) and k != "batch"]
+        f = {k: torch.cat([getattr(d, k) for d in data_list], 0) for k in keys
+             if all(hasattr(d, k) for d in data_list)}
+        f["batch"] = torch.repeat_interleave(torch.arange(f["natoms"].shape[0], device=f["pos"].device), f["natoms"])
+        f["sid"] = [s for d in data_list for s in d.sid]
+        return cls(**f)
+
 
 def make_system(system_id: int, adsorbate: str | None = None, jitter: float = 0.05,
                 size=(4, 4, 5), height: float = 2.0, skew: float = 0.0):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ADK_ABI_VERSION 1
+#define ADK_ABI_VERSION 2
 
 #define ADK_EINVAL (-22)   /* bad argument (null pointer, unsupported size) */
 #define ADK_ERANGE (-34)   /* size beyond a compiled capacity (images, atoms per system) */
@@ -38,6 +38,7 @@ extern "C" {
                                        (models/painn/painn_denoising.py:370-375) */
 #define ADK_STATUS_ROW_OVERFLOW 2u  /* an atom's in-degree exceeds ADK_MAX_ROW_DEGREE */
 
+#define ADK_STATUS_BAD_ELEMENT 8u   /* an atomic number outside [1, num_elements] (nn.Embedding would raise) */
 #define ADK_STATUS_F16_OVERFLOW 4u  /* a value left the fp16 range while being split for the tensor-core GEMM */
 
 #define ADK_MAX_IMAGES 2048        /* periodic images enumerated per system */
@@ -99,9 +100,11 @@ int adk_export_edges(const float* pos, const float* cell, const int32_t* atom_of
                      float* dist, float* unit_vec, int64_t* neighbors, void* stream);
 
 /* x[n] = emb[z[n]-1] ; vec = 0.  Replaces AtomEmbedding.forward
- * (models/gemnet_oc/layers/embedding_block.py:35-43) and painn_denoising.py:425-426. */
+ * (models/gemnet_oc/layers/embedding_block.py:35-43) and painn_denoising.py:425-426.
+ * An atomic number outside [1, num_elements] (nn.Embedding raises IndexError on it) sets
+ * ADK_STATUS_BAD_ELEMENT in *status (may be NULL). */
 int adk_embed(const int64_t* z, const float* emb, int num_elements, int N, int F,
-              float* x, float* vec, void* stream);
+              float* x, float* vec, uint32_t* status, void* stream);
 
 /* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5).  Replaces
  * PaiNNMessage.x_layernorm (painn_denoising.py:517,531). */
@@ -239,21 +242,39 @@ int adk_init_placement(float* pos, const float* cell, const int32_t* atom_off, c
                        const float* noise, int B, void* stream);
 
 /*
- * One reverse-diffusion ODE step on the rigid adsorbate of every system.
+ * One reverse-diffusion step (ODE or SDE) on the rigid adsorbate of every system.
  * Replaces DiffTorchCalc.get_denoising_prediction (denoising_torch.py:491-500), _get_ads_output
  * (:460-467), the update / PBC wrap / rigid rotation of reverse_sde_sampling_rot (:266-353) and
  * axis_angle_to_matrix (utils/rot_utils.py:18-98).
  *   score_tr/score_rot[N][3] = the two model outputs.
- *   sched[S][3] = per-step scalars (c_tr = 0.5*tr_g^2*dt, dt, rot_g2 = fp32(rot_g^2)); the row used is
- *   sched[*step], and *step (a device counter) is incremented afterwards, so a captured CUDA graph
- *   can be replayed for all S steps without host-side parameter updates.
- *   delta COM = c_tr * mean_tr (z zeroed), wrapped into the cell; rotation vector =
- *   ((0.5*mean_rot)*dt)*rot_g2.  pos updated in place; max_abs_upd[B] = max |delta COM| per system
- *   (for the reference's allclose early-stop, :312-320).
+ *   sched[S][ADK_SCHED_COLS] = per-step scalars, evaluated on the host with the reference's own expressions:
+ *     [0] 0.5*tr_g^2*dt  [1] dt  [2] fp32(rot_g^2)  [3] tr_g^2*dt  [4] tr_g*sqrt(dt)  [5] fp32(rot_g*sqrt(dt));
+ *   the row used is sched[*step], and *step (a device counter) is incremented afterwards, so a captured
+ *   CUDA graph can be replayed for all S steps without host-side parameter updates.
+ *   noise == NULL: ODE (`ode=True`, :269-272): delta COM = sched[0] * mean_tr (z zeroed), rotation vector =
+ *   ((0.5*mean_rot)*dt)*rot_g2.
+ *   noise[S][2][B][3]: SDE (`ode=False`, :273-295): noise[s][0] = tr_z and noise[s][1] = rot_z of step s, the
+ *   standard-normal draws the reference makes with torch.normal; delta COM = sched[3]*mean_tr + sched[4]*tr_z
+ *   (z zeroed), rotation vector = (mean_rot*dt)*rot_g2 + sched[5]*rot_z.
+ *   In both cases the COM is wrapped into the cell and the adsorbate moved rigidly; pos updated in place;
+ *   max_abs_upd[B] = max |delta COM| per system (for the reference's allclose early-stop, :312-320).
  */
+#define ADK_SCHED_COLS 6
 int adk_se3_step(float* pos, const float* cell, const int32_t* atom_off, const int32_t* tags,
                  const int32_t* fixed, const float* score_tr, const float* score_rot,
-                 const float* sched, int32_t* step, int B, float* max_abs_upd, void* stream);
+                 const float* sched, int32_t* step, int B, const float* noise /* NULL = ODE */,
+                 float* max_abs_upd, const int32_t* stop /* adk_early_stop state or NULL */, void* stream);
+
+/*
+ * Device-side form of the reference's batch-wide early stop (denoising_torch.py:312-320): after a step,
+ * allclose(delta COM, 0, rtol=1e-3, atol=1e-3) over all B systems (max_abs_upd from adk_se3_step) bumps
+ * stop[0]; at the tenth hit the reference breaks BEFORE applying that step, so stop[1] is raised, stop[2]
+ * records the number of applied steps and pos is restored from prev (the caller's copy of pos taken before
+ * the step).  Once stop[1] is set adk_se3_step leaves pos and *step untouched, so a host that polls stop[1]
+ * only every few steps still ends with exactly the reference's positions.  stop = int32[3], zeroed by the caller.
+ */
+int adk_early_stop(const float* max_abs_upd, int B, float atol, const int32_t* step, int32_t* stop,
+                   float* pos, const float* prev, int64_t n_values, void* stream);
 
 #ifdef __cplusplus
 }

@@ -122,31 +122,75 @@ def main():
         print(f"{name}: N={b.pos.shape[0]} E={ei.shape[1]} ties={g['n_ties']} stock==stable:{same} "
               f"|f1|max={float(f1.abs().max()):.4g}")
 
-    # ---- sampler: unmodified Denoiser.reverse_sde_sampling_rot, 8 steps, 2 systems --------------
-    from tests.cases import sampler_batch
+    sampler_goldens(ns, model)
 
-    b = sampler_batch()
-    ns.utils.radius_graph_pbc.__defaults__[-1][:] = [True, True, True]
-    # tamed output scale: see synthetic.random_state_dict(score_scale=...)
-    model.load_state_dict(S.random_state_dict(0, score_scale=S.SAMPLER_SCORE_SCALE), strict=True)
-    calc = ns.DiffTorchCalc(_FakeTrainer(model))
-    den = ns.Denoiser(b, calc, dict(SAMPLER_PARAMS), device="cpu", traj_dir=None, traj_names=b.sid)
+
+def run_reference_sampler(ns, model, b, params, seed):
+    """Drive the UNMODIFIED `Denoiser.reverse_sde_sampling_rot` on CPU.  Returns (init noise [B,3],
+    SDE noise [steps,2,B,3] or None, trajectory [steps,N,3], steps run).  The reference draws its random numbers
+    from the global CPU generator (:215 torch.rand, :274-289 torch.normal; the model forward draws none), so the
+    draws are reproduced by replaying the same call sequence after the same manual_seed."""
     import ase.io  # the inert shim
 
+    ns.utils.radius_graph_pbc.__defaults__[-1][:] = [True, True, True]
+    B, steps = b.num_graphs, params["num_steps"]
+    torch.manual_seed(seed)
+    noise = torch.rand(B, 3)
+    sde = None
+    if not params.get("ode", True):
+        sde = torch.stack([torch.stack([torch.normal(mean=0, std=1, size=(B, 3)),
+                                        torch.normal(mean=0, std=1, size=(B, 3))]) for _ in range(steps)])
+    calc = ns.DiffTorchCalc(_FakeTrainer(model))
+    den = ns.Denoiser(b, calc, dict(params), device="cpu", traj_dir=None, traj_names=b.sid)
     den.trajectories = [ase.io.Trajectory() for _ in b.sid]
-    torch.manual_seed(1234)
-    noise = torch.rand(b.num_graphs, 3)  # what :215 will draw
-    torch.manual_seed(1234)
+    torch.manual_seed(seed)
     den.reverse_sde_sampling_rot()
-    traj = []
-    for t in range(SAMPLER_PARAMS["num_steps"]):
-        traj.append(np.concatenate([tr.frames[t].kw["positions"] for tr in den.trajectories], 0))
-    np.savez_compressed(
-        os.path.join(OUT, "sampler.npz"), noise=noise.numpy(), traj=np.stack(traj).astype(np.float32),
-        final=b.pos.numpy(), params=np.array(repr(SAMPLER_PARAMS)),
-    )
-    print("sampler: steps", len(traj), "final pos checksum", float(b.pos.double().sum()))
+    n_run = len(den.trajectories[0].frames)
+    traj = [np.concatenate([tr.frames[t].kw["positions"] for tr in den.trajectories], 0) for t in range(n_run)]
+    return noise, sde, np.stack(traj).astype(np.float32), n_run
+
+
+def sampler_goldens(ns, model, only=None):
+    from tests.cases import sampler_batch, sampler100_batch
+
+    tamed = S.random_state_dict(0, score_scale=S.SAMPLER_SCORE_SCALE)
+    raw = S.random_state_dict(0)
+    full = dict(num_steps=100, ads_std_low=0.1, ads_std_high=10, rot_std_low=0.01, rot_std_high=1.55)
+    jobs = {
+        # name: (batch factory, weights, params, seed)
+        # tamed output scale: see synthetic.random_state_dict(score_scale=...)
+        "sampler": (sampler_batch, tamed, dict(SAMPLER_PARAMS), 1234),
+        # BASELINE config #1: ONE system, the shipped 100-step schedule (configs/denoising/painn_so3.yml:74-87)
+        "sampler100": (sampler100_batch, tamed, dict(full), 4321),
+        # the same with untamed random-init weights: a chaotic map, used step by step (teacher forcing)
+        "sampler100_raw": (sampler100_batch, raw, dict(full), 4321),
+        # SDE branch (ode=False): translation + rotation noise injected every step
+        "sampler_sde": (sampler_batch, tamed, dict(SAMPLER_PARAMS, num_steps=6, ode=False), 99),
+    }
+    for name, (make, sd, params, seed) in jobs.items():
+        if only and name not in only:
+            continue
+        b = make()
+        model.load_state_dict(sd, strict=True)
+        noise, sde, traj, n_run = run_reference_sampler(ns, model, b, params, seed)
+        rec = dict(noise=noise.numpy(), traj=traj, final=b.pos.numpy(), params=np.array(repr(params)),
+                   steps_run=np.array(n_run))
+        if sde is not None:
+            rec["sde_noise"] = sde.numpy()
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **rec)
+        print(f"{name}: steps {n_run}, final pos checksum {float(b.pos.double().sum()):.6f}")
 
 
 if __name__ == "__main__":
-    main()
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sampler-only", nargs="*", default=None,
+                    help="regenerate only the named sampler fixtures (e.g. sampler100 sampler_sde)")
+    a = ap.parse_args()
+    if a.sampler_only is not None:
+        ns_ = ref_import.load()
+        m_ = ns_.PaiNN(None, 0, 1, scale_file=ns_.scale_file, so3_denoising=True).eval()
+        sampler_goldens(ns_, m_, only=a.sampler_only or None)
+    else:
+        main()

@@ -353,16 +353,24 @@ def init_placement(pos, cell, batch, tags, noise):
     return pos
 
 
-def se3_step(pos, cell, batch, tags, fixed, score_tr, score_rot, tr_g, rot_g, dt):
-    """One ODE reverse step (denoising_torch.py:263-353, `ode=True`).  Returns (new_pos, delta_com)."""
+def se3_step(pos, cell, batch, tags, fixed, score_tr, score_rot, tr_g, rot_g, dt, tr_z=None, rot_z=None):
+    """One reverse step (denoising_torch.py:263-353).  `tr_z`/`rot_z` None: the ODE branch (`ode=True`, :269-272);
+    given ([B,3] standard-normal draws): the SDE branch (`ode=False`, :273-295), same torch expressions as the
+    reference so that dtype promotion (rot_g is float64, everything else fp32) is the reference's.
+    Returns (new_pos, delta_com)."""
     ads = tags == 2
     nsys = cell.shape[0]
     score_rot = score_rot.clone()
     score_rot[fixed == 1] = 0  # DiffTorchCalc.get_denoising_prediction :498
     npred = _ads_mean(score_tr, batch, ads, nsys)
     rpred = _ads_mean(score_rot, batch, ads, nsys)
-    upd = 0.5 * tr_g**2 * dt * npred
-    rotv = 0.5 * rpred * dt * rot_g**2  # float64 because rot_g is (:249-255)
+    if tr_z is None:
+        upd = 0.5 * tr_g**2 * dt * npred
+        rotv = 0.5 * rpred * dt * rot_g**2
+    else:
+        sqrt_dt = torch.sqrt(dt)  # np.sqrt(dt) on a 0-dim fp32 tensor returns a 0-dim fp32 tensor
+        upd = tr_g**2 * dt * npred + tr_g * sqrt_dt * tr_z
+        rotv = rpred * dt * rot_g**2 + rot_g * sqrt_dt * rot_z
     com = _ads_mean(pos, batch, ads, nsys)
     upd[:, -1] = 0
     frac = torch.linalg.solve(cell, com + upd)
@@ -378,8 +386,9 @@ def se3_step(pos, cell, batch, tags, fixed, score_tr, score_rot, tr_g, rot_g, dt
     return new_pos, upd
 
 
-def sample(P, batch_fields, params, noise, num_steps=None, model_kw=None, record=None):
-    """`Denoiser.reverse_sde_sampling_rot` with early stop disabled (fixed step count)."""
+def sample(P, batch_fields, params, noise, num_steps=None, model_kw=None, record=None, sde_noise=None):
+    """`Denoiser.reverse_sde_sampling_rot` with early stop disabled (fixed step count).
+    `sde_noise` [steps,2,B,3] (tr_z, rot_z per step) runs the SDE branch (`ode=False`)."""
     model_kw = model_kw or {}
     pos = batch_fields["pos"].clone().float()
     cell, bvec = batch_fields["cell"].float(), batch_fields["batch"]
@@ -390,7 +399,8 @@ def sample(P, batch_fields, params, noise, num_steps=None, model_kw=None, record
     for t in range(steps):
         tr_g, rot_g, dt = schedule(t, params)
         s_tr, s_rot = painn_forward(P, z, pos.numpy(), cell.numpy(), natoms, **model_kw)
-        pos, _ = se3_step(pos, cell, bvec, tags, fixed, s_tr, s_rot, tr_g, rot_g, dt)
+        zs = (None, None) if sde_noise is None else (sde_noise[t, 0], sde_noise[t, 1])
+        pos, _ = se3_step(pos, cell, bvec, tags, fixed, s_tr, s_rot, tr_g, rot_g, dt, *zs)
         if record is not None:
             record.append(pos.clone())
     return pos

@@ -30,3 +30,8 @@ CASES = {
 
 def sampler_batch():
     return S.make_batch(2, first_id=20)
+
+
+def sampler100_batch():
+    """BASELINE config #1: a single adsorbate+slab system for the full 100-step schedule."""
+    return S.make_batch(1, first_id=30)
