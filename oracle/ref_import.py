@@ -21,12 +21,36 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("ADSORBDIFF_REF", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
 
 
+def _find_root() -> str:
+    """Where the unmodified reference package lives: $ADSORBDIFF_REF, the mounted tree of the build container, or
+    the git-ignored `pip install --target baseline/_ref` copy that travels to the GPU box with the snapshot
+    (made by `__graft_entry__.build()`; never committed)."""
+    for cand in (os.environ.get("ADSORBDIFF_REF"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "adsorbdiff", "models", "painn")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
+
+
 def available() -> bool:
-    return os.path.isdir(os.path.join(REF_ROOT, "adsorbdiff"))
+    return os.path.isdir(os.path.join(REF_ROOT, "adsorbdiff", "models", "painn"))
+
+
+def scale_file():
+    """The shipped fitted scale factors: the reference's `.pt` when the source tree is there, else the same six
+    values as a dict (the pip-installed package carries no `configs/`; `load_scales_compat` takes a dict too)."""
+    path = os.path.join(REF_ROOT, "configs/scaling_factors/painn_nb6_scaling_factors.pt")
+    if os.path.exists(path):
+        return path
+    from adsorbdiff_b200.synthetic import SHIPPED_SCALE_FACTORS
+
+    return {f"upd_out_scalar_scale_{i}": float(v) for i, v in enumerate(SHIPPED_SCALE_FACTORS)}
 
 
 def _stub_package(name: str, path: str) -> None:
@@ -82,6 +106,7 @@ def load():
         Denoiser=denoising_torch.Denoiser,
         DiffTorchCalc=denoising_torch.DiffTorchCalc,
         axis_angle_to_matrix=rot_utils.axis_angle_to_matrix,
-        scale_file=os.path.join(REF_ROOT, "configs/scaling_factors/painn_nb6_scaling_factors.pt"),
+        scale_file=scale_file(),
+        root=REF_ROOT,
     )
     return ns

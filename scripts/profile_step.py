@@ -28,7 +28,7 @@ max_upd = torch.zeros(systems, dtype=torch.float32, device=dev)
 for _ in range(steps):
     model._run(plan, z, pos)
     _cabi.call("adk_se3_step", dev, _cabi.ptr(pos), _cabi.ptr(plan.cell_f32), _cabi.ptr(plan.atom_off), _cabi.ptr(tags), _cabi.ptr(fixed),
-               _cabi.ptr(plan.out[0]), _cabi.ptr(plan.out[1]), _cabi.ptr(sched), _cabi.ptr(step), systems, _cabi.ptr(max_upd))
+               _cabi.ptr(plan.out[0]), _cabi.ptr(plan.out[1]), _cabi.ptr(sched), _cabi.ptr(step), systems, None, _cabi.ptr(max_upd), None)
 torch.cuda.synchronize()
 model.check_status(plan)
 print("ok", systems, steps)

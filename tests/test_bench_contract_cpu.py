@@ -15,7 +15,7 @@ def test_reference_arm_prints_the_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "denoising_system_steps_per_sec"
-    assert d["unit"] == "system*steps/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["unit"] == "system*steps/s" and d["higher_is_better"] is True and d["scaling"] == "strong"
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["vs_baseline"] is None
     assert "workload" in d["config"] and not any(k in d["config"] for k in ("model", "seq_len", "global_batch"))
     cb, e2e = d["cpu_baseline"], d["e2e"]

@@ -104,5 +104,5 @@ def test_embed_matches_torch():
     emb = torch.randn(83, 128, generator=g).to(DEV)
     z = torch.randint(1, 84, (50,), generator=g).to(DEV)
     x = torch.empty(50, 128, device=DEV)
-    call("adk_embed", DEV, ptr(z), ptr(emb), 83, 50, 128, ptr(x), None)
+    call("adk_embed", DEV, ptr(z), ptr(emb), 83, 50, 128, ptr(x), None, None)
     assert torch.equal(x, emb[z - 1])                                       # embedding_block.py:42
