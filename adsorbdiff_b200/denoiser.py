@@ -230,14 +230,11 @@ class Denoiser:
                 else:
                     one_step()  # first step eager: warms every kernel up outside capture
                     if self.use_cuda_graph and num_steps > 2:
-                        torch.cuda.synchronize(dev)
-                        net.check_status(plan)
-                        graph = torch.cuda.CUDAGraph()
+                        net.check_status(plan)  # (a device synchronisation: one D2H read)
                         # Between the EMA swap-in above and the swap-out below nobody else writes the parameters,
                         # and the eager step just produced their fp16x2 planes: the replayed step does not redo it.
                         # (capture does not execute: pos / step / stop keep their values)
-                        with torch.cuda.graph(graph):
-                            one_step(weights_ready=True)
+                        graph = _cabi.capture_graph(lambda: one_step(weights_ready=True), dev)
                 t_idx += 1
                 if record:
                     self.frames[t_idx - 1].copy_(pos)

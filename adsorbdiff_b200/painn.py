@@ -702,11 +702,7 @@ class PaiNN(nn.Module):
             p.g_z = torch.empty_like(z)
             p.g_pos.copy_(pos)
             p.g_z.copy_(z)
-            torch.cuda.synchronize(p.device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._run(p, p.g_z, p.g_pos)
-            st["graph"] = g
+            st["graph"] = _cabi.capture_graph(lambda: self._run(p, p.g_z, p.g_pos), p.device)
         p.g_pos.copy_(pos)
         p.g_z.copy_(z)
         st["graph"].replay()

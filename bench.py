@@ -302,9 +302,8 @@ class StepLoop:
         self.launches_per_step = _cabi.launch_count - l0
         torch.cuda.synchronize(dev)
         model.check_status(self.plan)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.one_step(pruned)  # the sampler owns the parameters for its run: planes prepared once
+        # (pruned: the sampler owns the parameters for its run, the weight operand planes are prepared once)
+        self.graph = _cabi.capture_graph(lambda: self.one_step(pruned), dev)
         self.done = 1
 
     def one_step(self, weights_ready):

@@ -116,8 +116,9 @@ def test_config1_raw_weights_every_step_teacher_forced(golden, weights):
 # ------------------------------------------------------------------ SDE branch
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_sde_branch_matches_reference(golden, sampler_weights, use_graph):
-    """`ode=False` (denoising_torch.py:273-295) with the normal draws the reference made: 1e-6 A after one step,
-    1e-5 A at every step."""
+    """`ode=False` (denoising_torch.py:273-295) with the normal draws the reference made.  The injected translation
+    noise is ~12 A x N(0,1) at the first steps, so adsorbate coordinates sit in [16, 32) A where ONE fp32 ulp is
+    1.9e-6 A: the bar is 2e-6 A (one ulp) after the first step and 1e-5 A at every step."""
     _reset_sticky_pbc()
     g = golden("sampler_sde")
     params = ast.literal_eval(str(g["params"]))
@@ -129,7 +130,7 @@ def test_sde_branch_matches_reference(golden, sampler_weights, use_graph):
     den.run()
     errs = np.abs(den.frames.cpu().numpy() - g["traj"]).max(axis=(1, 2))
     print("sde: max |dpos| per step:", " ".join("%.1e" % e for e in errs))
-    assert errs[0] < 1e-6
+    assert errs[0] <= 2e-6
     assert errs.max() < 1e-5
     # and the noise really is in play: the ODE run from the same start ends somewhere else
     b2 = sampler_batch().to(DEV)
