@@ -12,7 +12,7 @@ extern "C" int adk_init(void) {
     if ((rc = adk_message_set_attrs()) != 0) return rc;
     if ((rc = adk_linear_set_attrs()) != 0) return rc;
     if ((rc = adk_linear_tc_set_attrs()) != 0) return rc;
-    if ((rc = adk_message_tc_set_attrs()) != 0) return rc;
     if ((rc = adk_message_mma_set_attrs()) != 0) return rc;
+    if ((rc = adk_message_t5_set_attrs()) != 0) return rc;
     return 0;
 }

@@ -62,5 +62,5 @@ int adk_neighbors_set_attrs();
 int adk_message_set_attrs();
 int adk_linear_set_attrs();
 int adk_linear_tc_set_attrs();
-int adk_message_tc_set_attrs();
 int adk_message_mma_set_attrs();
+int adk_message_t5_set_attrs();

@@ -16,9 +16,8 @@
 // column) are multiplied by the staged xh / vec of the edge's source atom and accumulated per lane;
 // one shuffle reduction per target row finishes the segmented sum.  No atomics, deterministic.
 //
-// tcgen05 was tried for this contraction first (csrc/message_tc.cu: TMEM accumulators, TMA-streamed
-// weights, generator warps writing the UMMA operand layout): parity-green but 2.7x slower than the
-// SIMT kernel because a thread-per-feature epilogue has to gather per edge from L2.
+// The tcgen05 kernel (csrc/message_t5.cu) is the default; this one serves the shapes it does not take (other
+// num_rbf, hidden % 64 != 0, systems whose staged sources exceed its shared memory).
 // Reference arithmetic: models/gemnet_oc/layers/radial_basis.py:235-244, models/painn/painn_denoising.py:534-567, 443-445.
 #include <cuda_fp16.h>
 

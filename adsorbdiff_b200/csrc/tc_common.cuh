@@ -84,6 +84,21 @@ __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t* v) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16 consecutive columns of this thread's TMEM lane, no wait
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+// after tmem_ld_wait(): ties the loaded registers to this point of the instruction stream, so that no use of them
+// can be scheduled above the wait (the asynchronous load writes them behind the compiler's back)
+__device__ __forceinline__ void tmem_pin16(uint32_t* v) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                      "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+}
 
 // ---- CTA-pair (cta_group::2) forms: the two CTAs of a 2-cluster issue one MMA over M = 256; each stages its own
 // A rows and HALF of the B tile, which halves the operand bytes an SM has to pull in per k-block.

@@ -209,10 +209,13 @@ class PaiNN(nn.Module):
         self._plan_cache: Optional[_Plan] = None
         # "tc": tcgen05 fp16x2-split GEMMs (fp32 parity, see csrc/linear_tc.cu); "fp32": exact-fp32 SIMT GEMMs
         self.gemm = "tc"
-        # message kernel: "mma" = per-system staged, rbf_proj as warp-level mma.sync micro-GEMMs
-        # (csrc/message_mma.cu); "simt" = 16-tap FFMA2 kernel (csrc/message.cu); "tc" = tcgen05 experiment
-        # (csrc/message_tc.cu, parity-green but gather-latency bound)
-        self.msg = "mma"
+        # message kernel: "t5" = tcgen05 / TMEM / TMA kernel with the system's sources staged in shared memory
+        # (csrc/message_t5.cu; needs num_rbf == 128, hidden % 64 == 0 and systems of <= ~110 atoms -- anything else
+        # falls through to "mma", then "simt"); "mma" = per-system staged, rbf_proj as
+        # warp-level mma.sync micro-GEMMs (csrc/message_mma.cu); "simt" = 16-tap FFMA2 kernel (csrc/message.cu)
+        self.msg = "t5"
+        self.msg_t5_comp = 0.0  # accumulate-truncation compensation of the t5 kernel
+        self.t5_min_ctas = 0   # (bring-up knob: use the t5 kernel only from this many CTAs on)
         self.msg_comp = 1.1920929e-07  # accumulate-truncation compensation of the message MMA (calibrated)
         self._wsplit_cache: dict = {}
 
@@ -344,6 +347,12 @@ class PaiNN(nn.Module):
         # does a system's staged slice fit the shared memory of the warp-MMA message kernel?  (else: adk_message)
         p.mma_fits = (self.num_rbf % 16 == 0 and 16 <= self.num_rbf <= 128
                       and _cabi.load().adk_message_mma_smem_bytes(self.num_rbf, p.n_max) > 0)
+        # tcgen05 message kernel: 8 slice-CTAs per system; below ~2 CTAs per SM the row-split mma kernel wins
+        # (the kernel evaluates the Gaussian centres arithmetically as k / (R - 1): check the buffer really is that)
+        off = self.radial_basis.rbf.offset
+        uniform = bool(torch.equal(off.detach().cpu(), torch.linspace(0.0, 1.0, self.num_rbf)))
+        p.t5_fits = (self.num_rbf == 128 and F % 64 == 0 and p.B * (F // 64) >= self.t5_min_ctas and uniform
+                     and _cabi.load().adk_message_t5_smem_bytes(self.num_rbf, p.n_max) > 0)
         self._plan_cache = p
         return p
 
@@ -489,7 +498,7 @@ class PaiNN(nn.Module):
         whatever they held.  The rows that are written are bit-identical to the full evaluation."""
         N, F, R = p.N, self.hidden_channels, self.num_rbf
         dev = p.device
-        if (self.gemm == "tc" or self.msg == "tc") and not weights_ready:
+        if (self.gemm == "tc" or self.msg == "t5") and not weights_ready:
             self._resplit_weights(p)
         self._graph(p, pos)
         call("adk_embed", dev, ptr(z), ptr(self.atom_emb.embeddings.weight), self.atom_emb.embeddings.weight.shape[0],
@@ -519,22 +528,35 @@ class PaiNN(nn.Module):
             vin = p.vec[cur] if l > 0 else None  # vec == 0 before the first message
             vout = p.vec[1 - cur]
             vec_presplit = False
-            if self.msg == "mma" and p.mma_fits:
+            # row selection of the sampler's tail: the last layer is evaluated at out_rows only, so the layer before
+            # it is needed only at those rows and at the sources of their in-edges (other rows pass vec through)
+            pruned = out_rows is not None and l == self.num_layers - 1 and trace is None
+            row_sel = out_rows[1] if pruned else None
+            if out_rows is not None and trace is None and l == self.num_layers - 2:
+                if getattr(p, "sel2", None) is None:
+                    p.sel2 = torch.empty(N, dtype=torch.int32, device=dev)
+                call("adk_mark_sources", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(out_rows[0]),
+                     int(out_rows[0].numel()), N, ptr(p.sel2))
+                row_sel = p.sel2
+            if self.msg == "t5" and p.t5_fits:
+                planes = self._tc_ok(u.vec_proj) and not pruned
+                call("adk_message_t5", dev, ptr(p.atom_off), p.B, p.n_max, ptr(row_sel) if row_sel is not None else None,
+                     ptr(p.row_start), ptr(p.row_deg),
+                     ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None,
+                     ptr(self._wsplit(p, m.rbf_proj)), self.W_SCALE, ptr(m.rbf_proj.bias),
+                     ptr(self.radial_basis.rbf.offset), F, R, float(self.cutoff), self.radial_basis.exponent,
+                     float(self.msg_t5_comp), ptr(p.x), ptr(vout), ptr(p.sp_v) if planes else None, p.rows_3n,
+                     self.V_SCALE, ptr(p.status))
+                vec_presplit = planes
+                if pruned:
+                    self._finish_rows(p, out_rows[0], l, vout)
+                    return
+            elif self.msg in ("mma", "t5") and p.mma_fits:
                 wt = p.wt_rbf[l]
                 if not weights_ready:
                     call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self.W_SCALE, ptr(wt),
                          ptr(p.status))
-                pruned = out_rows is not None and l == self.num_layers - 1 and trace is None
                 planes = self._tc_ok(u.vec_proj) and not pruned
-                row_sel = out_rows[1] if pruned else None
-                if out_rows is not None and trace is None and l == self.num_layers - 2:
-                    # the last layer is evaluated at out_rows only, so THIS layer's messages are needed only at those
-                    # rows and at the sources of their in-edges; every other row passes vec through unchanged
-                    if getattr(p, "sel2", None) is None:
-                        p.sel2 = torch.empty(N, dtype=torch.int32, device=dev)
-                    call("adk_mark_sources", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(out_rows[0]),
-                         int(out_rows[0].numel()), N, ptr(p.sel2))
-                    row_sel = p.sel2
                 call("adk_message_mma", dev, ptr(p.atom_off), p.B, p.n_max, ptr(row_sel) if row_sel is not None else None,
                      ptr(p.row_start), ptr(p.row_deg),
                      ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wt),
@@ -545,12 +567,6 @@ class PaiNN(nn.Module):
                 if pruned:
                     self._finish_rows(p, out_rows[0], l, vout)
                     return
-            elif self.msg == "tc" and F == 512 and R == 128:
-                wr = self._wsplit(p, m.rbf_proj)
-                call("adk_message_tc", dev, ptr(p.atom_off), p.B, ptr(p.sys_counts), ptr(p.row_deg), ptr(p.e_src),
-                     ptr(p.e_tgt), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wr),
-                     self.W_SCALE, ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R, self.max_neighbors,
-                     float(self.cutoff), self.radial_basis.exponent, float(self.msg_comp), ptr(p.x), ptr(vout))
             else:
                 call("adk_message", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(p.xh),
                      ptr(vin) if vin is not None else None, ptr(m.rbf_proj.weight), ptr(m.rbf_proj.bias),
@@ -679,7 +695,7 @@ class PaiNN(nn.Module):
     # ------------------------------------------------------------------ forward
     def _graph_key(self):
         """Everything a captured forward bakes in besides the plan: engine choices and every parameter address."""
-        return (self.gemm, self.msg, getattr(self, "gemm_heads", None), float(self.msg_comp),
+        return (self.gemm, self.msg, getattr(self, "gemm_heads", None), float(self.msg_comp), float(self.msg_t5_comp),
                 tuple(t.data_ptr() for t in self.parameters()), tuple(t.data_ptr() for t in self.buffers()))
 
     def _run_graphed(self, p: _Plan, z: torch.Tensor, pos: torch.Tensor) -> None:

@@ -164,19 +164,6 @@ int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t*
                 int envelope_exponent, float* x_io, float* vec_out, void* stream);
 
 /*
- * Tensor-core variant of adk_message: same contract, rbf_proj runs on tcgen05 (fp16x2 split, TMEM
- * accumulators, weights streamed by TMA), one CTA per system, epilogue threads own one feature and
- * reduce along the CSR row in registers.  Requires F == 512, R == 128.
- *   w_rbf_split = adk_split_f16(w_rbf[3F][R], scale = w_scale) -> fp16 [2][3F][R]
- *   comp = relative compensation of the tensor core's accumulate-truncation bias (see csrc/linear_tc.cu)
- */
-int adk_message_tc(const int32_t* atom_off, int B, const int32_t* sys_counts, const int32_t* row_deg,
-                   const int32_t* e_src, const int32_t* e_tgt, const float* e_geo, const float* xh,
-                   const float* vec_in, const void* w_rbf_split, float w_scale, const float* b_rbf,
-                   const float* rbf_offset, int F, int R, int max_nbrs, float cutoff,
-                   int envelope_exponent, float comp, float* x_io, float* vec_out, void* stream);
-
-/*
  * Warp-MMA variant of adk_message (csrc/message_mma.cu): one CTA per (system, 32-feature slice); the
  * system's xh / vec slices and the fp16x2 planes of the w_rbf slice are staged in shared memory, and
  * rbfh of 16 distance-sorted edges at a time is a mma.sync m16n8k16 micro-GEMM over the union RBF window.
@@ -198,6 +185,23 @@ int adk_message_mma(const int32_t* atom_off, int B, int n_max,
                     float comp, float* x_io, float* vec_out,
                     void* vec_split /* fp16 [2][split_rows][F], row = atom*3+xyz, or NULL */, int64_t split_rows,
                     float split_scale, uint32_t* status, void* stream);
+
+/*
+ * tcgen05 variant of adk_message_mma, the default for full batches (csrc/message_t5.cu): one CTA per (system,
+ * 64-feature slice); D[feature][edge] = W . rbf^T by tcgen05.mma into TMEM (fp16x2 split, banded K), weights by
+ * TMA, sources of the whole system staged in shared memory, epilogue threads own one feature (= TMEM lane) and
+ * reduce the CSR rows in registers.  Same arithmetic contract as adk_message; requires R == 128, F % 64 == 0 and a
+ * system that fits (adk_message_t5_smem_bytes > 0), else the caller uses adk_message_mma / adk_message.
+ *   w_rbf_split = fp16 [2][3F][R] planes of w_rbf scaled by w_scale (adk_split_f16_multi)
+ */
+int64_t adk_message_t5_smem_bytes(int R, int n_max);
+int adk_message_t5(const int32_t* atom_off, int B, int n_max,
+                   const int32_t* row_sel /* NULL, or [N] with the meaning it has for adk_message_mma */,
+                   const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const float* e_geo, const float* xh, const float* vec_in,
+                   const void* w_rbf_split, float w_scale, const float* b_rbf, const float* rbf_offset,
+                   int F, int R, float cutoff, int envelope_exponent, float comp, float* x_io, float* vec_out,
+                   void* vec_split /* fp16 [2][split_rows][F], row = atom*3+xyz, or NULL */, int64_t split_rows,
+                   float split_scale, uint32_t* status, void* stream);
 
 /* From vp[N][3][2F] = vec_proj(vec) = (vec1|vec2): dot[N][F] = sum_xyz vec1*vec2 / sqrt(F),
  * cat[N][2F] = [x | sqrt(sum_xyz vec2^2 + 1e-8)].  PaiNNUpdate.forward (painn_denoising.py:602-613). */

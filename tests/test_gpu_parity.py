@@ -71,7 +71,7 @@ def test_empty_system_raises_value_error(model):
 
 
 @pytest.mark.parametrize("name", ["jit2", "mixed", "tiny", "gas", "skew", "pbc_ttf"])
-@pytest.mark.parametrize("gemm,msg", [("tc", "mma"), ("tc", "tc"), ("tc", "simt"), ("fp32", "simt")])
+@pytest.mark.parametrize("gemm,msg", [("tc", "t5"), ("tc", "mma"), ("tc", "simt"), ("fp32", "simt")])
 def test_forward_matches_oracle_and_reference(name, gemm, msg, model, golden, weights):
     """Per-layer node features and both outputs, for both GEMM engines (tcgen05 fp16x2-split and
     exact-fp32 SIMT) and both message kernels (rbf_proj on tcgen05 / 16-tap SIMT).  Stated tolerance (all relative to the tensor's max magnitude):
@@ -95,7 +95,7 @@ def test_forward_matches_oracle_and_reference(name, gemm, msg, model, golden, we
     try:
         outs = model(_with_pbc(b.clone(), pbc).to("cuda:0"), trace=tr_c)
     finally:
-        model.gemm, model.msg = "tc", "mma"
+        model.gemm, model.msg = "tc", "t5"
     rel = lambda a, ref: float((a.double().cpu() - ref.double()).abs().max() / ref.double().abs().max())
     worst = 0.0
     for key in tr_c:

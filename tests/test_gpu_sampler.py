@@ -202,8 +202,9 @@ def test_small_angle_rotation_branch(sampler_weights):
     assert float(rotv) < 1e-6
     sched = schedule_table(params, dev)
     step = torch.full((1,), t, dtype=torch.int32, device=dev)
+    d_tr, d_rot = s_tr.to(dev), s_rot.to(dev)   # (named: the launch is asynchronous, temporaries would be recycled)
     call("adk_se3_step", dev, ptr(pos), ptr(plan.cell_f32), ptr(plan.atom_off), ptr(tags), ptr(fixed),
-         ptr(s_tr.to(dev)), ptr(s_rot.to(dev)), ptr(sched), ptr(step), plan.B, None, None, None)
+         ptr(d_tr), ptr(d_rot), ptr(sched), ptr(step), plan.B, None, None, None)
     assert int(step.item()) == t + 1
     np.testing.assert_allclose(pos.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-6)
 
