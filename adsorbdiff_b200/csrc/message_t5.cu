@@ -56,8 +56,11 @@ constexpr uint32_t T5_W_PLANE = 2 * T5_W_KBLOCK;
 constexpr uint32_t T5_W_BYTES = 2 * T5_W_PLANE;               // hi + lo: 64 KB
 constexpr uint32_t T5_B_PLANE = 128 * 128;                    // [128 columns][64 centres] fp16
 constexpr uint32_t T5_B_BYTES = 2 * T5_B_PLANE;               // hi + lo: 32 KB
-constexpr uint32_t T5_META_SRC = 0, T5_META_RHAT = 512, T5_META_CNT = 2560, T5_META_ROW = 2592;
-constexpr uint32_t T5_META_BYTES = 2688;
+// r_hat of a column PAIR = 8 floats (x0 x1 y0 y1 z0 z1 - -); after every four pairs 32 bytes of padding, so that the
+// generator lanes' stores (pairs 0, 4, 8, 12 of a warp) fall on different banks
+constexpr uint32_t T5_META_SRC = 0, T5_META_RHAT = 512, T5_META_CNT = 3072, T5_META_ROW = 3104;
+constexpr uint32_t T5_META_BYTES = 3200;
+__host__ __device__ constexpr uint32_t t5_rhat_off(int pair) { return (uint32_t)(pair * 32 + (pair >> 2) * 32); }
 constexpr uint32_t T5_SRC_PITCH_A = 2 * T5_SF * 4;            // [xh1 | xh3] per atom
 constexpr uint32_t T5_SRC_PITCH_B = 3 * T5_SF * 4;            // p2 = xh2 * vec[x|y|z] per atom
 constexpr float T5_RBF_SCALE = 1024.0f;
@@ -134,6 +137,9 @@ __device__ __forceinline__ bool tile_last(uint32_t t) { return (t >> 24) != 0u; 
 // before the arithmetic; an earlier version that loaded edge by edge spent ~65 cycles of exposed latency per four edges.
 // `v` holds the accumulator columns of this thread's feature.  Padding columns point at a zero source row, so no
 // per-edge predicates are needed.  p[c] = (sum over even edges, sum over odd edges) of output component c.
+#ifndef T5_EXP
+#define T5_EXP 0   // bring-up experiments (scripts/build_exp_libs.sh): 1 = no TMEM loads, 2 = no source loads, 3 = empty epilogue
+#endif
 template <int MODE, int NE>   // MODE 0: dx (m1), 1: m3 * r_hat, 2: p2 * m2
 __device__ __forceinline__ void edge_block(const uint32_t* v, const uint8_t* meta, int col, const uint8_t* src_lane,
                                            float2 scale2, float2 bias2, float2* p) {
@@ -148,13 +154,14 @@ __device__ __forceinline__ void edge_block(const uint32_t* v, const uint8_t* met
 #pragma unroll
     for (int e = 0; e < NE; ++e)
 #pragma unroll
-        for (int c = 0; c < W; ++c) x[e][c] = *reinterpret_cast<const float*>(src_lane + so[e] + c * T5_SF * 4);
+        for (int c = 0; c < W; ++c)
+            x[e][c] = (T5_EXP == 2) ? __int_as_float(so[e] + c) : *reinterpret_cast<const float*>(src_lane + so[e] + c * T5_SF * 4);
     float4 rxy[NE / 2];
     float2 rz[NE / 2];
     if (MODE == 1) {
 #pragma unroll
         for (int h = 0; h < NE / 2; ++h) {
-            const uint8_t* ra = meta + T5_META_RHAT + (size_t)((col >> 1) + h) * 32;
+            const uint8_t* ra = meta + T5_META_RHAT + t5_rhat_off((col >> 1) + h);
             rxy[h] = *reinterpret_cast<const float4*>(ra);        // x0 x1 y0 y1
             rz[h] = *reinterpret_cast<const float2*>(ra + 16);    // z0 z1
         }
@@ -201,8 +208,13 @@ __device__ __forceinline__ void tile_body(uint32_t t_addr, const uint8_t* meta, 
     for (int i = 0; i < NS; ++i) {
         if (cnt[i] > 0) {   // warp-uniform
             uint32_t v[16];
-            tmem_ld16_async(t_addr + (uint32_t)(s0 + i) * T5_SLOT, v);
-            tmem_ld_wait();
+            if (T5_EXP == 1) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = t_addr + k;
+            } else {
+                tmem_ld16_async(t_addr + (uint32_t)(s0 + i) * T5_SLOT, v);
+                tmem_ld_wait();
+            }
             tmem_pin16(v);
             float2 p[W];
 #pragma unroll
@@ -404,24 +416,36 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                         last = s_item[buf * 4 + 2] != 0;
                         // descriptors differ in their low word only: (address >> 4) | constant bits
                         const uint32_t bh_lo = desc_lo(b_smem + buf * T5_B_BYTES), bl_lo = bh_lo + (T5_B_PLANE >> 4);
+                        // All descriptor words first (independent integer work), then the tcgen05.mma of the item
+                        // in straight-line code per k-step count: the issuing thread, not the tensor pipe, paces a
+                        // tile (~100 cycles per MMA when descriptor arithmetic and branches sit between them).
+                        uint32_t a_lo[4];
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            const int k = kbase + 16 * s;
+                            a_lo[s] = wh_lo + (uint32_t)(k >> 6) * (T5_W_KBLOCK >> 4) + (uint32_t)((k >> 3) & 7);
+                        }
+                        const uint32_t acc0 = first ? 0u : 1u;
                         // corrections first (while the accumulator is small), then the hi x hi products
-#pragma unroll
-                        for (int s = 0; s < 4; ++s) {
-                            if (s < nks) {
-                                const int k = kbase + 16 * s;
-                                const uint32_t ah_lo = wh_lo + (uint32_t)(k >> 6) * (T5_W_KBLOCK >> 4) + (uint32_t)((k >> 3) & 7);
-                                umma_f16(d_tmem, mk_desc(ah_lo), mk_desc(bl_lo + 2 * s), idesc, (first && s == 0) ? 0u : 1u);
-                                umma_f16(d_tmem, mk_desc(ah_lo + (T5_W_PLANE >> 4)), mk_desc(bh_lo + 2 * s), idesc, 1u);
-                            }
+#define T5_MMA_CORR(s, acc)                                                                                         \
+    umma_f16(d_tmem, mk_desc(a_lo[s]), mk_desc(bl_lo + 2 * (s)), idesc, acc);                                      \
+    umma_f16(d_tmem, mk_desc(a_lo[s] + (T5_W_PLANE >> 4)), mk_desc(bh_lo + 2 * (s)), idesc, 1u);
+#define T5_MMA_MAIN(s) umma_f16(d_tmem, mk_desc(a_lo[s]), mk_desc(bh_lo + 2 * (s)), idesc, 1u);
+                        if (nks == 4) {
+                            T5_MMA_CORR(0, acc0) T5_MMA_CORR(1, 1u) T5_MMA_CORR(2, 1u) T5_MMA_CORR(3, 1u)
+                            T5_MMA_MAIN(0) T5_MMA_MAIN(1) T5_MMA_MAIN(2) T5_MMA_MAIN(3)
+                        } else if (nks == 3) {
+                            T5_MMA_CORR(0, acc0) T5_MMA_CORR(1, 1u) T5_MMA_CORR(2, 1u)
+                            T5_MMA_MAIN(0) T5_MMA_MAIN(1) T5_MMA_MAIN(2)
+                        } else if (nks == 2) {
+                            T5_MMA_CORR(0, acc0) T5_MMA_CORR(1, 1u)
+                            T5_MMA_MAIN(0) T5_MMA_MAIN(1)
+                        } else {
+                            T5_MMA_CORR(0, acc0)
+                            T5_MMA_MAIN(0)
                         }
-#pragma unroll
-                        for (int s = 0; s < 4; ++s) {
-                            if (s < nks) {
-                                const int k = kbase + 16 * s;
-                                const uint32_t ah_lo = wh_lo + (uint32_t)(k >> 6) * (T5_W_KBLOCK >> 4) + (uint32_t)((k >> 3) & 7);
-                                umma_f16(d_tmem, mk_desc(ah_lo), mk_desc(bh_lo + 2 * s), idesc, 1u);
-                            }
-                        }
+#undef T5_MMA_CORR
+#undef T5_MMA_MAIN
                         umma_commit(b_empty(buf));
                         first = false;
                         ++items[buf];
@@ -445,6 +469,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
         const float rmax = (float)(R - 1);
         const float h0 = 1.0f / rmax;   // centre spacing (the host checked that rbf_offset is linspace(0, 1, R))
         uint32_t items[T5_BBUFS] = {0u, 0u};   // operand tiles written per buffer (tile ti uses buffer ti % T5_BBUFS)
+        uint32_t dirty[T5_BBUFS] = {0xffu, 0xffu};   // 16-byte chunks of MY row of a buffer that may hold non-zeros (all, at first)
         // the CSR record of this column for tile ti (padding: source row n = zeros)
         auto fetch = [&](int ti, int& src, float4& geo, int& deg_out, int& row_out) {
             src = n;
@@ -536,7 +561,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                 {
                     uint8_t* mg = gbase + (meta_smem - base) + ds * T5_META_BYTES;
                     reinterpret_cast<int*>(mg + T5_META_SRC)[c] = src * pitch;
-                    float* rh = reinterpret_cast<float*>(mg + T5_META_RHAT) + (c >> 1) * 8 + (c & 1);   // x0 x1 y0 y1 z0 z1 - -
+                    float* rh = reinterpret_cast<float*>(mg + T5_META_RHAT + t5_rhat_off(c >> 1)) + (c & 1);   // x0 x1 y0 y1 z0 z1 - -
                     rh[0] = geo.y; rh[2] = geo.z; rh[4] = geo.w;
                     if (j == 0) {
                         reinterpret_cast<int*>(mg + T5_META_CNT)[slot] = max(0, min(T5_SLOT, deg - tile_chunk(tl) * T5_SLOT));
@@ -552,24 +577,30 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                     if (gw == 0 && sub == 0) T5_STAMP(ti, 3);
                     const uint32_t bb = b_smem + buf * T5_B_BYTES + row_off;
                     const int q0 = (kb - k8) >> 3;   // my 8-block qq sits in chunk qq - q0 of this operand row
-                    // zeros where none of my three blocks falls, then the blocks (static register indices)
-#pragma unroll
-                    for (int ch = 0; ch < 8; ++ch) {
-                        if (ch < 2 * nks && (unsigned)(ch + q0) >= 3u) {
-                            const uint32_t addr = bb + (uint32_t)((ch ^ (c & 7)) * 16);
-                            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
-                            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr + T5_B_PLANE), "r"(0u) : "memory");
-                        }
-                    }
+                    // my three 8-blocks (static register indices) ...
+                    uint32_t valued = 0u;
 #pragma unroll
                     for (int qq = 0; qq < 3; ++qq) {
                         const int ch = qq - q0;
                         if (ch >= 0 && ch < 2 * nks) {
+                            valued |= 1u << ch;
                             const uint32_t addr = bb + (uint32_t)((ch ^ (c & 7)) * 16);
                             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hi[4 * qq]), "r"(hi[4 * qq + 1]), "r"(hi[4 * qq + 2]), "r"(hi[4 * qq + 3]) : "memory");
                             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr + T5_B_PLANE), "r"(lo[4 * qq]), "r"(lo[4 * qq + 1]), "r"(lo[4 * qq + 2]), "r"(lo[4 * qq + 3]) : "memory");
                         }
                     }
+                    // ... and zeros only where this row of the buffer still holds values of an earlier tile (the 16
+                    // unconditional zero stores per tile were a tenth of the kernel's shared-memory wavefronts)
+                    const uint32_t stale = dirty[buf] & ~valued & ((1u << (2 * nks)) - 1u);
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        if ((stale >> ch) & 1u) {
+                            const uint32_t addr = bb + (uint32_t)((ch ^ (c & 7)) * 16);
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr + T5_B_PLANE), "r"(0u) : "memory");
+                        }
+                    }
+                    dirty[buf] = (dirty[buf] & ~stale) | valued;
                     if (c == 0) {
                         s_item[buf * 4] = kb;
                         s_item[buf * 4 + 1] = nks;
@@ -623,7 +654,8 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                 if (warp == T5_EPI_WARP0 + 2) T5_STAMP(ti, 9);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ds * T5_TILE;
-                if (phase == 0) {
+                if (T5_EXP == 3) {
+                } else if (phase == 0) {
                     if (!upper) tile_body<0, 4>(t_addr, meta_g, src_lane, scale2, bias2, s0, acc);
                     else tile_body<1, 4>(t_addr, meta_g, src_lane, scale2, bias2, s0, acc);
                 } else {

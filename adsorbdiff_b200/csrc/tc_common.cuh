@@ -20,17 +20,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    // try_wait parks the thread until the phase completes or the time limit passes.  With the (short) default limit a
-    // waiting warp re-issued the loop constantly: a quarter of all instructions of the message kernel were these
-    // spins, taken from the working warps' issue slots.  A long limit costs nothing: completion still wakes the thread.
     uint32_t ok;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(bar), "r"(parity), "r"(1000000u)
+            : "r"(bar), "r"(parity)
             : "memory");
     } while (!ok);
 }

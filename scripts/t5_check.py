@@ -2,6 +2,9 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from adsorbdiff_b200 import _cabi
+if os.environ.get("ADK_LIB"):
+    _cabi._LIB_PATH = os.environ["ADK_LIB"]
 from adsorbdiff_b200 import PaiNN, synthetic as S
 
 dev = torch.device("cuda:0")
@@ -13,16 +16,16 @@ base = [S.make_system(i) for i in range(min(64, nsys))]
 b = S.collate([base[i % len(base)] for i in range(nsys)]).to(dev)
 m.t5_min_ctas = 0
 res = {}
-for eng in ("mma", "t5"):
+for eng in (() if os.environ.get("T5_TIME_ONLY") else ("mma", "t5")):
     m.msg = eng
     tr = {}
     o = m(b, trace=tr)
     torch.cuda.synchronize()
     res[eng] = (o, tr)
 rel = lambda a, r: float((a.double() - r.double()).abs().max() / r.double().abs().max())
-for k in res["mma"][1]:
+for k in (res["mma"][1] if res else ()):
     print(f"{k:10s} t5 vs mma: {rel(res['t5'][1][k], res['mma'][1][k]):.3e}")
-for i in range(2):
+for i in (range(2) if res else ()):
     print("out", i, rel(res["t5"][0][i], res["mma"][0][i]))
 if len(sys.argv) > 2:
     from oracle import painn_oracle as O
