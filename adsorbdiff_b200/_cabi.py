@@ -68,6 +68,10 @@ class AdkError(RuntimeError):
     pass
 
 
+class AdkOverflow(AdkError):
+    """STATUS_F16_OVERFLOW: an operand exceeded the fp16 range under the current prescales."""
+
+
 _lib = None
 _inited_devices: set[int] = set()
 launch_count = 0  # kernels launched through this binding (bench.py reports it)

@@ -391,9 +391,12 @@ struct SplitDesc {
     const float* src;
     __half* dst;
     int64_t n;
+    float scale;   // this tensor's power-of-two prescale; 0 = the launch-wide default
+    int32_t pad;
 };
-__global__ void split_f16_multi_kernel(const SplitDesc* __restrict__ table, float scale, uint32_t* status) {
+__global__ void split_f16_multi_kernel(const SplitDesc* __restrict__ table, float default_scale, uint32_t* status) {
     const SplitDesc d = table[blockIdx.y];
+    const float scale = d.scale != 0.0f ? d.scale : default_scale;
     bool overflow = false;
     const int64_t n4 = d.n >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {

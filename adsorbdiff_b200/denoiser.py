@@ -173,6 +173,10 @@ class Denoiser:
             ema.copy_to()
         net.eval()
         try:
+            # operand prescales of the tensor-core GEMMs: measured on the weights that will actually run (the EMA
+            # shadow, if any, was just swapped in) and on a sample of this batch
+            if net.auto_calibrate and (ema or net._needs_calibration()):
+                net.calibrate(batch)
             plan, z, pos = net._prepare(batch)
             if pos.data_ptr() != batch.pos.data_ptr():
                 batch.pos = pos  # fp32 contiguous working copy becomes the batch's positions

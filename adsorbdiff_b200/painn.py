@@ -133,6 +133,27 @@ class _Plan:
     pass
 
 
+class _SubBatch:
+    """The first systems of a batch (views, no copies): what `PaiNN.calibrate` evaluates."""
+
+    pass
+
+
+def _first_systems(data, k: int):
+    natoms = data.natoms
+    nat = (natoms if torch.is_tensor(natoms) else torch.as_tensor([int(natoms)] if not hasattr(natoms, "__len__") else natoms)).view(-1)
+    if nat.numel() <= k:
+        return data
+    n = int(nat[:k].sum())
+    sub = _SubBatch()
+    sub.pos, sub.cell, sub.natoms = data.pos[:n], data.cell[:k], nat[:k].clone()
+    sub.atomic_numbers = data.atomic_numbers[:n]
+    pbc = getattr(data, "pbc", None)
+    if pbc is not None:
+        sub.pbc = pbc[:k] if torch.is_tensor(pbc) and pbc.dim() == 2 else pbc
+    return sub
+
+
 class PaiNN(nn.Module):
     def __init__(
         self,
@@ -207,6 +228,10 @@ class PaiNN(nn.Module):
                 else:
                     logging.warning(f"Scale factor {name} not found in model")
         self._plan_cache: Optional[_Plan] = None
+        self._scales: Optional[dict] = None   # calibrated fp16x2 prescales (see `calibrate`); None = class defaults
+        self._calib: Optional[dict] = None    # while calibrating: id(linear) -> max |input|
+        self.auto_calibrate = True
+        self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, "_scales", None))
         # "tc": tcgen05 fp16x2-split GEMMs (fp32 parity, see csrc/linear_tc.cu); "fp32": exact-fp32 SIMT GEMMs
         self.gemm = "tc"
         # message kernel: "t5" = tcgen05 / TMEM / TMA kernel with the system's sources staged in shared memory
@@ -368,10 +393,66 @@ class PaiNN(nn.Module):
     A_SCALE = 16.0
     V_SCALE = 1024.0
     W_SCALE = 1024.0
+    # Those three are the UNCALIBRATED defaults (right for Xavier-scale weights and O(1) features).  `calibrate`
+    # replaces them by one power-of-two scale per GEMM operand -- per weight tensor and per activation site --
+    # measured on the model's own weights and a sample of the caller's data with the exact-fp32 engine.
+    SCALE_TARGET = 2048.0   # scaled magnitudes are placed here: 32x below the fp16 limit, lo plane normal down to 2^-14 of it
+
+    def _sa(self, lin, default):
+        """Prescale of the A-operand planes that feed `lin`."""
+        sc = self._scales
+        return sc["a"].get(id(lin), default) if sc else default
+
+    def _sw(self, lin):
+        sc = self._scales
+        return sc["w"].get(id(lin), self.W_SCALE) if sc else self.W_SCALE
+
+    @staticmethod
+    def _pow2_scale(amax: float, target: float) -> float:
+        if not (amax > 0.0) or not math.isfinite(amax):
+            return 1.0
+        return float(2.0 ** max(-20, min(24, math.floor(math.log2(target / amax)))))
+
+    @torch.no_grad()
+    def calibrate(self, data, max_systems: int = 16) -> dict:
+        """Choose the fp16x2 prescales from the model's weights and from the activations of `data` (its first
+        `max_systems` systems), evaluated once with the exact-fp32 SIMT GEMMs.  Called automatically by the first
+        tensor-core forward after construction / `load_state_dict`, by `Denoiser` after its EMA swap-in, and on an
+        fp16-overflow status; call it yourself after changing parameters in place by a large factor."""
+        sub = _first_systems(data, max_systems)
+        amax_a: dict = {}
+        saved = (self.gemm, getattr(self, "gemm_heads", None), self.msg, self._plan_cache, self._calib)
+        # exact-fp32 engines only: SIMT GEMMs and the SIMT message kernel (nothing in this pass can overflow)
+        self.gemm, self.gemm_heads, self.msg, self._calib = "fp32", None, "simt", amax_a
+        try:
+            p, z, pos = self._prepare(sub)
+            self._run(p, z, pos)
+            self.check_status(p)
+        finally:
+            self.gemm, self.gemm_heads, self.msg, self._plan_cache, self._calib = saved
+        a = {k: self._pow2_scale(v, self.SCALE_TARGET) for k, v in amax_a.items()}
+        # operand planes shared by several GEMMs carry one scale: the smallest of their consumers'
+        heads = [self.out_forces] + ([self.out_forces2] if self.so3_denoising else [])
+        groups = [[q for h in heads for q in (h.output_network[0].vec1_proj, h.output_network[0].vec2_proj)]]
+        groups += [[h.output_network[1].vec1_proj, h.output_network[1].vec2_proj] for h in heads]
+        for grp in groups:
+            vals = [a[id(q)] for q in grp if id(q) in a]
+            if vals:
+                for q in grp:
+                    a[id(q)] = min(vals)
+        w = {id(l): self._pow2_scale(float(l.weight.detach().abs().max()), self.SCALE_TARGET) for l in self._tc_linears()}
+        self._scales = {"a": a, "w": w}
+        self._wsplit_cache.pop("table", None)   # the records carry the weight scales
+        return self._scales
+
 
     def _linear(self, p, A, lda, lin, M, act, C, ldc):
         """Exact-fp32 SIMT GEMM (also the path for the 1- and 2-column head outputs)."""
         W = lin.weight
+        if self._calib is not None:   # calibration pass: record the magnitude of this GEMM's input
+            K = W.shape[1]
+            view = torch.as_strided(A, (M, K), (lda, 1), A.storage_offset())
+            self._calib[id(lin)] = max(self._calib.get(id(lin), 0.0), float(view.abs().max()))
         call("adk_linear", p.device, ptr(A), lda, ptr(W), ptr(lin.bias) if lin.bias is not None else None,
              M, W.shape[0], W.shape[1], act, ptr(C), ldc)
 
@@ -404,12 +485,15 @@ class PaiNN(nn.Module):
         key = tuple(l.weight.data_ptr() for l in lins)
         st = self._wsplit_cache.get("table")
         if st is None or st[0] != key or st[1].device != p.device:
+            import struct
+
             bufs, recs = {}, []
             for l in lins:
                 n = l.weight.numel()
                 buf = torch.empty(2 * n, dtype=torch.float16, device=p.device)
                 bufs[id(l)] = buf
-                recs += [l.weight.data_ptr(), buf.data_ptr(), n]
+                scale_bits = struct.unpack("<q", struct.pack("<fi", float(self._sw(l)), 0))[0]
+                recs += [l.weight.data_ptr(), buf.data_ptr(), n, scale_bits]
             table = torch.tensor(recs, dtype=torch.int64).to(p.device)
             st = (key, table, bufs, len(lins))
             self._wsplit_cache["table"] = st
@@ -418,18 +502,22 @@ class PaiNN(nn.Module):
     def _wsplit(self, p, lin):
         return self._wsplit_cache["table"][2][id(lin)]
 
-    def _split(self, p, A, lda, M, K, buf, rows, scale=None):
-        call("adk_split_f16", p.device, ptr(A), lda, M, K, scale or self.A_SCALE, ptr(buf), rows, ptr(p.status))
+    def _split(self, p, A, lda, M, K, buf, rows, scale):
+        call("adk_split_f16", p.device, ptr(A), lda, M, K, scale, ptr(buf), rows, ptr(p.status))
 
     def _linear_tc(self, p, a_split, a_rows, M, lin, act, out_f32=None, ldc=0, out_split=None, out_rows=0,
-                   a_scale=None):
+                   a_default=None, out_lin=None):
+        """`a_default`: class default of the input planes' prescale (A_SCALE / V_SCALE); `out_lin`: the GEMM that
+        consumes the emitted output planes (their prescale is that GEMM's input prescale)."""
         W = lin.weight
         N, K = W.shape
         ws = self._wsplit(p, lin)
+        a_scale = self._sa(lin, a_default or self.A_SCALE)
+        out_scale = self._sa(out_lin, self.A_SCALE) if out_lin is not None else self.A_SCALE
         call("adk_linear_tc", p.device, ptr(a_split), a_rows, M, ptr(ws), N, K,
-             ptr(lin.bias) if lin.bias is not None else None, 1.0 / ((a_scale or self.A_SCALE) * self.W_SCALE), act,
+             ptr(lin.bias) if lin.bias is not None else None, 1.0 / (a_scale * self._sw(lin)), act,
              ptr(out_f32) if out_f32 is not None else None, ldc,
-             ptr(out_split) if out_split is not None else None, out_rows, self.A_SCALE, ptr(p.status))
+             ptr(out_split) if out_split is not None else None, out_rows, out_scale, ptr(p.status))
 
     def _mlp2(self, p, A, lda, M, K, lin0, lin1, out, ldc, presplit=False, ws=None):
         """out = lin1(ssilu(lin0(A))): the two-layer MLP shape shared by x_proj, xvec_proj and update_net.
@@ -438,9 +526,9 @@ class PaiNN(nn.Module):
         sp_in, sp_hid, rows, h1 = ws if ws is not None else (p.sp_x, p.sp_h, p.rows_n, p.h1)
         if self._tc_ok(lin0):
             if not presplit:
-                self._split(p, A, lda, M, K, sp_in, rows)
+                self._split(p, A, lda, M, K, sp_in, rows, self._sa(lin0, self.A_SCALE))
             if self._tc_ok(lin1):
-                self._linear_tc(p, sp_in, rows, M, lin0, _cabi.ACT_SSILU, out_split=sp_hid, out_rows=rows)
+                self._linear_tc(p, sp_in, rows, M, lin0, _cabi.ACT_SSILU, out_split=sp_hid, out_rows=rows, out_lin=lin1)
                 self._linear_tc(p, sp_hid, rows, M, lin1, _cabi.ACT_NONE, out_f32=out, ldc=ldc)
             else:
                 self._linear_tc(p, sp_in, rows, M, lin0, _cabi.ACT_SSILU, out_f32=h1, ldc=lin0.weight.shape[0])
@@ -455,11 +543,11 @@ class PaiNN(nn.Module):
         M = 3 * p.N
         planes = p.sp_v if planes is None else planes
         if not presplit and any(self._tc_ok(lin) for lin, _ in lins_outs):
-            self._split(p, vec, K, M, K, planes, p.rows_3n, self.V_SCALE)
+            self._split(p, vec, K, M, K, planes, p.rows_3n, self._sa(lins_outs[0][0], self.V_SCALE))
         for lin, out in lins_outs:
             n_out = lin.weight.shape[0]
             if self._tc_ok(lin):
-                self._linear_tc(p, planes, p.rows_3n, M, lin, _cabi.ACT_NONE, out_f32=out, ldc=n_out, a_scale=self.V_SCALE)
+                self._linear_tc(p, planes, p.rows_3n, M, lin, _cabi.ACT_NONE, out_f32=out, ldc=n_out, a_default=self.V_SCALE)
             else:
                 self._linear(p, vec, K, lin, M, _cabi.ACT_NONE, out, n_out)
 
@@ -472,16 +560,16 @@ class PaiNN(nn.Module):
         self._vec_linear(p, vec, F, [(b0.vec1_proj, p.v1p), (b0.vec2_proj, p.v2p)], presplit=presplit)
         tc = self._tc_ok(b0.update_net[0])
         call("adk_head_prep", dev, ptr(x), ptr(p.v1p), N, F, None if tc else ptr(p.cat), ptr(p.sp_x) if tc else None,
-             p.rows_n, self.A_SCALE, ptr(p.status))
+             p.rows_n, self._sa(b0.update_net[0], self.A_SCALE), ptr(p.status))
         self._mlp2(p, p.cat, 2 * F, N, 2 * F, b0.update_net[0], b0.update_net[2], p.xn, F, presplit=tc)  # (s|g)
         hv_tc = any(self._tc_ok(l) for l in (b1.vec1_proj, b1.vec2_proj)) and H % 4 == 0
         call("adk_head_gate", dev, ptr(p.xn), ptr(p.v2p), N, H, ptr(p.hx), ptr(p.hv),
-             ptr(p.sp_hv) if hv_tc else None, p.rows_3n, self.V_SCALE, ptr(p.status))
+             ptr(p.sp_hv) if hv_tc else None, p.rows_3n, self._sa(b1.vec1_proj, self.V_SCALE), ptr(p.status))
         # block 1: H -> 1
         self._vec_linear(p, p.hv, H, [(b1.vec1_proj, p.v1p), (b1.vec2_proj, p.v2p2)], presplit=hv_tc, planes=p.sp_hv)
         tc = self._tc_ok(b1.update_net[0])
         call("adk_head_prep", dev, ptr(p.hx), ptr(p.v1p), N, H, None if tc else ptr(p.cat), ptr(p.sp_x) if tc else None,
-             p.rows_n, self.A_SCALE, ptr(p.status))
+             p.rows_n, self._sa(b1.update_net[0], self.A_SCALE), ptr(p.status))
         self._mlp2(p, p.cat, 2 * H, N, 2 * H, b1.update_net[0], b1.update_net[2], p.ho2, 2, presplit=tc)
         call("adk_head_gate", dev, ptr(p.ho2), ptr(p.v2p2), N, 1, None, ptr(out), None, 0, 0.0, ptr(p.status))
 
@@ -516,14 +604,14 @@ class PaiNN(nn.Module):
                 ne = E.shape[0]
                 call("adk_layernorm", dev, ptr(E), ptr(m.x_layernorm.weight), ptr(m.x_layernorm.bias), ne, F,
                      float(m.x_layernorm.eps), None if tc else ptr(p.tab_y), ptr(p.tab_spx) if tc else None, p.tab_rows,
-                     self.A_SCALE, ptr(p.status))
+                     self._sa(m.x_proj[0], self.A_SCALE), ptr(p.status))
                 self._mlp2(p, p.tab_y, F, ne, F, m.x_proj[0], m.x_proj[2], p.tab_xh, 3 * F, presplit=tc,
                            ws=(p.tab_spx, p.tab_sph, p.tab_rows, p.tab_h1))
                 call("adk_embed", dev, ptr(z), ptr(p.tab_xh), ne, N, 3 * F, ptr(p.xh), None, None)
             else:
                 call("adk_layernorm", dev, ptr(p.x), ptr(m.x_layernorm.weight), ptr(m.x_layernorm.bias), N, F,
                      float(m.x_layernorm.eps), None if tc else ptr(p.xn), ptr(p.sp_x) if tc else None, p.rows_n,
-                     self.A_SCALE, ptr(p.status))
+                     self._sa(m.x_proj[0], self.A_SCALE), ptr(p.status))
                 self._mlp2(p, p.xn, F, N, F, m.x_proj[0], m.x_proj[2], p.xh, 3 * F, presplit=tc)
             vin = p.vec[cur] if l > 0 else None  # vec == 0 before the first message
             vout = p.vec[1 - cur]
@@ -543,10 +631,10 @@ class PaiNN(nn.Module):
                 call("adk_message_t5", dev, ptr(p.atom_off), p.B, p.n_max, ptr(row_sel) if row_sel is not None else None,
                      ptr(p.row_start), ptr(p.row_deg),
                      ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None,
-                     ptr(self._wsplit(p, m.rbf_proj)), self.W_SCALE, ptr(m.rbf_proj.bias),
+                     ptr(self._wsplit(p, m.rbf_proj)), self._sw(m.rbf_proj), ptr(m.rbf_proj.bias),
                      ptr(self.radial_basis.rbf.offset), F, R, float(self.cutoff), self.radial_basis.exponent,
                      float(self.msg_t5_comp), ptr(p.x), ptr(vout), ptr(p.sp_v) if planes else None, p.rows_3n,
-                     self.V_SCALE, ptr(p.status))
+                     self._sa(u.vec_proj, self.V_SCALE), ptr(p.status))
                 vec_presplit = planes
                 if pruned:
                     self._finish_rows(p, out_rows[0], l, vout)
@@ -554,15 +642,15 @@ class PaiNN(nn.Module):
             elif self.msg in ("mma", "t5") and p.mma_fits:
                 wt = p.wt_rbf[l]
                 if not weights_ready:
-                    call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self.W_SCALE, ptr(wt),
+                    call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self._sw(m.rbf_proj), ptr(wt),
                          ptr(p.status))
                 planes = self._tc_ok(u.vec_proj) and not pruned
                 call("adk_message_mma", dev, ptr(p.atom_off), p.B, p.n_max, ptr(row_sel) if row_sel is not None else None,
                      ptr(p.row_start), ptr(p.row_deg),
                      ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wt),
-                     self.W_SCALE, ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R,
+                     self._sw(m.rbf_proj), ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R,
                      float(self.cutoff), self.radial_basis.exponent, float(self.msg_comp), ptr(p.x), ptr(vout),
-                     ptr(p.sp_v) if planes else None, p.rows_3n, self.V_SCALE, ptr(p.status))
+                     ptr(p.sp_v) if planes else None, p.rows_3n, self._sa(u.vec_proj, self.V_SCALE), ptr(p.status))
                 vec_presplit = planes
                 if pruned:
                     self._finish_rows(p, out_rows[0], l, vout)
@@ -589,14 +677,14 @@ class PaiNN(nn.Module):
         self._vec_linear(p, vec, F, [(u.vec_proj, p.vp)], presplit=vec_presplit)
         tc = self._tc_ok(u.xvec_proj[0])
         call("adk_update_prep", dev, ptr(p.x), ptr(p.vp), N, F, ptr(p.dot), None if tc else ptr(p.cat),
-             ptr(p.sp_x) if tc else None, p.rows_n, self.A_SCALE, ptr(p.status))
+             ptr(p.sp_x) if tc else None, p.rows_n, self._sa(u.xvec_proj[0], self.A_SCALE), ptr(p.status))
         self._mlp2(p, p.cat, 2 * F, N, 2 * F, u.xvec_proj[0], u.xvec_proj[2], p.xh, 3 * F, presplit=tc)
         sc = getattr(self, "upd_out_scalar_scale_%d" % l).scale_factor
         # the last layer's update also writes the fp16x2 planes of vec that both heads' vec projections read
         b0 = self.out_forces.output_network[0]
         emit = l == self.num_layers - 1 and any(self._tc_ok(q) for q in (b0.vec1_proj, b0.vec2_proj))
         call("adk_update_gate", dev, ptr(p.xh), ptr(p.dot), ptr(p.vp), ptr(sc), N, F, ptr(p.x), ptr(vec),
-             ptr(p.sp_v) if emit else None, p.rows_3n, self.V_SCALE, ptr(p.status))
+             ptr(p.sp_v) if emit else None, p.rows_3n, self._sa(b0.vec1_proj, self.V_SCALE), ptr(p.status))
         return emit
 
     def _heads(self, p, vec: torch.Tensor, heads_presplit: bool) -> None:
@@ -689,13 +777,15 @@ class PaiNN(nn.Module):
         if st & _cabi.STATUS_ROW_OVERFLOW:
             raise _cabi.AdkError("an atom's in-degree exceeds ADK_MAX_ROW_DEGREE")
         if st & _cabi.STATUS_F16_OVERFLOW:
-            raise _cabi.AdkError("a value left the fp16 range in the fp16x2 split of the tensor-core GEMM "
-                                 "(|16*scalar feature|, |1024*vector feature| or |1024*weight| > 65504); set model.gemm = 'fp32'")
+            raise _cabi.AdkOverflow("a scaled operand of a tensor-core GEMM left the fp16 range (fp16x2 split): the "
+                                    "prescales chosen by PaiNN.calibrate no longer fit the weights / activations -- "
+                                    "call model.calibrate(batch) again, or set model.gemm = 'fp32'")
 
     # ------------------------------------------------------------------ forward
     def _graph_key(self):
         """Everything a captured forward bakes in besides the plan: engine choices and every parameter address."""
         return (self.gemm, self.msg, getattr(self, "gemm_heads", None), float(self.msg_comp), float(self.msg_t5_comp),
+                id(self._scales),
                 tuple(t.data_ptr() for t in self.parameters()), tuple(t.data_ptr() for t in self.buffers()))
 
     def _run_graphed(self, p: _Plan, z: torch.Tensor, pos: torch.Tensor) -> None:
@@ -725,15 +815,29 @@ class PaiNN(nn.Module):
 
     forward_graph = True  # capture the public forward as a CUDA graph from the second call on a plan (see above)
 
+    def _needs_calibration(self) -> bool:
+        return self.auto_calibrate and self._scales is None and self._calib is None and (self.gemm == "tc" or self.msg == "t5")
+
     def forward(self, data, trace: Optional[dict] = None):
         self._refuse_training()
         with torch.no_grad():
-            p, z, pos = self._prepare(data)
-            if trace is None and self.forward_graph and not torch.cuda.is_current_stream_capturing():
-                self._run_graphed(p, z, pos)
-            else:
-                self._run(p, z, pos, trace)
-            self.check_status(p)
+            if self._needs_calibration():
+                self.calibrate(data)
+            for attempt in range(2):
+                p, z, pos = self._prepare(data)
+                if trace is None and self.forward_graph and not torch.cuda.is_current_stream_capturing():
+                    self._run_graphed(p, z, pos)
+                else:
+                    self._run(p, z, pos, trace)
+                try:
+                    self.check_status(p)
+                    break
+                except _cabi.AdkOverflow:
+                    # an operand left the fp16 range under the present prescales (weights or activations have grown
+                    # since they were chosen): measure again on this batch and repeat the forward once
+                    if attempt or not self.auto_calibrate:
+                        raise
+                    self.calibrate(data)
             if not self.so3_denoising:
                 return p.out[0].clone()
             return p.out[0].clone(), p.out[1].clone()

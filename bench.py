@@ -284,6 +284,8 @@ class StepLoop:
         self.model, self.batch = model, batch
         dev = batch.pos.device
         self.dev = dev
+        if model._needs_calibration():
+            model.calibrate(batch)   # (what the public forward / Denoiser do on first use)
         self.plan, self.z, self.pos = model._prepare(batch)
         self.tags = batch.tags.to(torch.int32).contiguous()
         self.fixed = batch.fixed.to(torch.int32).contiguous()

@@ -138,7 +138,8 @@ int adk_split_f16(const float* src, int64_t ld, int M, int K, float scale, void*
 int adk_set_tc_pair(int enable);
 
 /* Same split for `count` contiguous tensors in one launch: table[i] = {const float* src; fp16* dst;
- * int64 n_elems} (device array of 24-byte records; dst planes are n_elems apart, n_elems % 4 == 0).
+ * int64 n_elems; float scale; int32 pad} (device array of 32-byte records; dst planes are n_elems apart,
+ * n_elems % 4 == 0; scale = that tensor's prescale, 0 = the `scale` argument).
  * Used to re-split every weight at the start of each forward, so in-place parameter updates
  * (EMA swaps through `.data`, optimizer steps) can never leave a stale packed copy behind. */
 int adk_split_f16_multi(const void* table, int count, float scale, uint32_t* status, void* stream);

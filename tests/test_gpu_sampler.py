@@ -294,3 +294,56 @@ def test_denoiser_accepts_ddp_wrapped_model(sampler_weights):
 def test_row_overflow_publishes_empty_row_status():
     """Advisor item: the status word and ABI constants stay in sync with the header."""
     assert _cabi.STATUS_BAD_ELEMENT == 8 and _cabi.SCHED_COLS == 6
+
+
+# ------------------------------------------------------------------ calibrated fp16x2 prescales
+def test_prescales_follow_trained_scale_weights_and_features(weights):
+    """The tensor-core GEMMs split fp32 operands into two fp16 planes after a power-of-two prescale.  The prescales are
+    measured (`PaiNN.calibrate`) on the loaded weights and a sample of the data, so a checkpoint far from Xavier scale
+    keeps fp32 parity: weights of the message / update MLPs x 30, embedding x 8 (node scalars O(20), vec O(100)).
+    With the uncalibrated class defaults this network overflows the fp16 range; calibrated it meets the 1e-5 bar
+    against the fp64 oracle, without a status bit."""
+    _reset_sticky_pbc()
+    sd = {k: v.clone() for k, v in weights.items()}
+    for k in sd:
+        if "rbf_proj.weight" in k or "vec_proj.weight" in k:
+            sd[k] = sd[k] * 30.0
+        if k == "atom_emb.embeddings.weight":
+            sd[k] = sd[k] * 8.0
+    b = S.make_batch(2, first_id=60)
+    o64 = O.painn_forward(sd, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms, dtype=torch.float64)
+    m = _model(sd)
+    assert m._scales is None                     # load_state_dict reset them
+    bd = b.clone().to(DEV)
+    outs = m(bd)                                 # calibrates on first use
+    assert m._scales is not None
+    vmax = float(m._plan_cache.vec[0].abs().max())
+    print(f"scaled network: max |vec| {vmax:.1f}; weight prescales {sorted(set(m._scales['w'].values()))}, "
+          f"activation prescales {sorted(set(m._scales['a'].values()))}")
+    for got, ref in zip(outs, o64):
+        err = float((got.double().cpu() - ref).abs().max() / ref.abs().max())
+        assert err < 1e-5, err
+    # the class defaults really are out of range here: the status bit fires and the forward re-calibrates by itself
+    m._scales = {"a": {}, "w": {}}               # (every lookup falls back to the defaults)
+    m.auto_calibrate = False
+    with pytest.raises(_cabi.AdkOverflow):
+        m(bd)
+    m.auto_calibrate = True
+    again = m(bd)
+    assert len(m._scales["w"]) > 0 and torch.equal(again[0], outs[0])
+
+
+def test_denoiser_catches_overflow_early(sampler_weights):
+    """An operand leaving the fp16 range is reported after the first replayed step, not at the end of the run."""
+    _reset_sticky_pbc()
+    m = _model(sampler_weights)
+    params = dict(num_steps=50, ads_std_low=0.1, ads_std_high=10, rot_std_low=0.01, rot_std_high=1.55, early_stop=False)
+    b = sampler_batch().to(DEV)
+    m.calibrate(b)
+    m.auto_calibrate = False
+    with torch.no_grad():
+        m.message_layers[0].rbf_proj.weight.mul_(1e4)   # in place, behind the prescales' back
+    den = Denoiser(b, m, params, device=DEV)
+    with pytest.raises(_cabi.AdkOverflow):
+        den.run()
+    assert den.steps_run == 0    # raised inside the loop (first status check), long before step 50
