@@ -482,7 +482,7 @@ class PaiNN(nn.Module):
         any time -- the reference's EMA does `param.data.copy_()` three times per sampler step, which does
         not even bump `Parameter._version` -- so no cache keyed on versions can be trusted."""
         lins = self._tc_linears()
-        key = tuple(l.weight.data_ptr() for l in lins)
+        key = (tuple(l.weight.data_ptr() for l in lins), id(self._scales))
         st = self._wsplit_cache.get("table")
         if st is None or st[0] != key or st[1].device != p.device:
             import struct
