@@ -56,11 +56,10 @@ constexpr uint32_t T5_W_PLANE = 2 * T5_W_KBLOCK;
 constexpr uint32_t T5_W_BYTES = 2 * T5_W_PLANE;               // hi + lo: 64 KB
 constexpr uint32_t T5_B_PLANE = 128 * 128;                    // [128 columns][64 centres] fp16
 constexpr uint32_t T5_B_BYTES = 2 * T5_B_PLANE;               // hi + lo: 32 KB
-// r_hat of a column PAIR = 8 floats (x0 x1 y0 y1 z0 z1 - -); after every four pairs 32 bytes of padding, so that the
-// generator lanes' stores (pairs 0, 4, 8, 12 of a warp) fall on different banks
-constexpr uint32_t T5_META_SRC = 0, T5_META_RHAT = 512, T5_META_CNT = 3072, T5_META_ROW = 3104;
-constexpr uint32_t T5_META_BYTES = 3200;
-__host__ __device__ constexpr uint32_t t5_rhat_off(int pair) { return (uint32_t)(pair * 32 + (pair >> 2) * 32); }
+// r_hat of a block of eight columns = 24 floats [x0..x7 | y0..y7 | z0..z7]: the generator lanes' stores are conflict
+// free (stride 24 words across blocks) and an edge block reads its unit vectors with six 16-byte loads
+constexpr uint32_t T5_META_SRC = 0, T5_META_RHAT = 512, T5_META_CNT = 2048, T5_META_ROW = 2080;
+constexpr uint32_t T5_META_BYTES = 2176;
 constexpr uint32_t T5_SRC_PITCH_A = 2 * T5_SF * 4;            // [xh1 | xh3] per atom
 constexpr uint32_t T5_SRC_PITCH_B = 3 * T5_SF * 4;            // p2 = xh2 * vec[x|y|z] per atom
 constexpr float T5_RBF_SCALE = 1024.0f;
@@ -156,14 +155,14 @@ __device__ __forceinline__ void edge_block(const uint32_t* v, const uint8_t* met
 #pragma unroll
         for (int c = 0; c < W; ++c)
             x[e][c] = (T5_EXP == 2) ? __int_as_float(so[e] + c) : *reinterpret_cast<const float*>(src_lane + so[e] + c * T5_SF * 4);
-    float4 rxy[NE / 2];
-    float2 rz[NE / 2];
+    float4 rx[NE / 4], ry[NE / 4], rz[NE / 4];
     if (MODE == 1) {
+        const float4* ra = reinterpret_cast<const float4*>(meta + T5_META_RHAT + (size_t)(col >> 3) * 96 + (size_t)(col & 7) * 4);
 #pragma unroll
-        for (int h = 0; h < NE / 2; ++h) {
-            const uint8_t* ra = meta + T5_META_RHAT + t5_rhat_off((col >> 1) + h);
-            rxy[h] = *reinterpret_cast<const float4*>(ra);        // x0 x1 y0 y1
-            rz[h] = *reinterpret_cast<const float2*>(ra + 16);    // z0 z1
+        for (int i = 0; i < NE / 4; ++i) {
+            rx[i] = ra[i];
+            ry[i] = ra[2 + i];
+            rz[i] = ra[4 + i];
         }
     }
 #pragma unroll
@@ -173,9 +172,10 @@ __device__ __forceinline__ void edge_block(const uint32_t* v, const uint8_t* met
             p[0] = adk::fma2(make_float2(x[2 * h][0], x[2 * h + 1][0]), r2, p[0]);
         } else if (MODE == 1) {
             const float2 m2 = adk::fma2(make_float2(x[2 * h][0], x[2 * h + 1][0]), r2, make_float2(0.f, 0.f));
-            p[0] = adk::fma2(m2, make_float2(rxy[h].x, rxy[h].y), p[0]);
-            p[1] = adk::fma2(m2, make_float2(rxy[h].z, rxy[h].w), p[1]);
-            p[2] = adk::fma2(m2, rz[h], p[2]);
+            const float4 qx = rx[h >> 1], qy = ry[h >> 1], qz = rz[h >> 1];
+            p[0] = adk::fma2(m2, (h & 1) ? make_float2(qx.z, qx.w) : make_float2(qx.x, qx.y), p[0]);
+            p[1] = adk::fma2(m2, (h & 1) ? make_float2(qy.z, qy.w) : make_float2(qy.x, qy.y), p[1]);
+            p[2] = adk::fma2(m2, (h & 1) ? make_float2(qz.z, qz.w) : make_float2(qz.x, qz.y), p[2]);
         } else {
 #pragma unroll
             for (int c = 0; c < 3; ++c) p[c] = adk::fma2(make_float2(x[2 * h][c], x[2 * h + 1][c]), r2, p[c]);
@@ -561,8 +561,8 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                 {
                     uint8_t* mg = gbase + (meta_smem - base) + ds * T5_META_BYTES;
                     reinterpret_cast<int*>(mg + T5_META_SRC)[c] = src * pitch;
-                    float* rh = reinterpret_cast<float*>(mg + T5_META_RHAT + t5_rhat_off(c >> 1)) + (c & 1);   // x0 x1 y0 y1 z0 z1 - -
-                    rh[0] = geo.y; rh[2] = geo.z; rh[4] = geo.w;
+                    float* rh = reinterpret_cast<float*>(mg + T5_META_RHAT) + (c >> 3) * 24 + (c & 7);   // [x0..7 | y0..7 | z0..7]
+                    rh[0] = geo.y; rh[8] = geo.z; rh[16] = geo.w;
                     if (j == 0) {
                         reinterpret_cast<int*>(mg + T5_META_CNT)[slot] = max(0, min(T5_SLOT, deg - tile_chunk(tl) * T5_SLOT));
                         reinterpret_cast<int*>(mg + T5_META_ROW)[slot] = row;
