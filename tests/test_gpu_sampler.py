@@ -10,6 +10,7 @@
 Tolerances are written at every assert (Angstrom).
 """
 import ast
+import os
 
 import numpy as np
 import pytest
@@ -364,3 +365,61 @@ def test_denoiser_catches_overflow_early(sampler_weights):
     with pytest.raises(_cabi.AdkOverflow):
         den.run()
     assert den.steps_run == 0    # raised inside the loop (first status check), long before step 50
+
+
+# ------------------------------------------------------------------ caller side: packed input -> batch driver
+def test_batch_driver_from_packed_input_matches_direct_sampling(sampler_weights, tmp_path):
+    """`run_diffusion_batches` over a `PackedLoader` (pinned, prefetched batches; 2 placements per system) gives, system
+    by system, what `Denoiser` gives on the same batch with the same initial-placement draws; the merged result file
+    has the reference's keys; trajectories are written, and a second run skips every batch (resume)."""
+    from adsorbdiff_b200 import PackedLoader, PackedSystems, run_diffusion_batches
+
+    _reset_sticky_pbc()
+    params = dict(num_steps=3, ads_std_low=0.1, ads_std_high=10, rot_std_low=0.01, rot_std_high=1.55, early_stop=False)
+    systems = [S.make_system(70 + i) for i in range(4)]
+    pk = PackedSystems.from_data_list(systems)
+    pk.save(tmp_path / "pk")
+    loader = PackedLoader(PackedSystems.load(tmp_path / "pk"), systems_per_batch=2, placements=2)
+    m = _model(sampler_weights)
+    torch.manual_seed(21)                       # the sampler draws torch.rand(B, 3) per batch on the CPU generator
+    out = run_diffusion_batches(m, loader, params, device=DEV, traj_dir=tmp_path / "traj", results_dir=tmp_path / "res")
+    assert out["ids"].tolist() == sorted(f"{i}_p{r}" for i in range(4) for r in range(2))
+    # the same two batches through Denoiser directly
+    torch.manual_seed(21)
+    ref = {}
+    for chunk in ([0, 1], [2, 3]):
+        b = S.collate([systems[i] for i in chunk for _ in range(2)], sids=[f"{i}_p{r}" for i in chunk for r in range(2)]).to(DEV)
+        Denoiser(b, m, params, device=DEV).run()
+        for sid, p in zip(b.sid, torch.split(b.pos.cpu(), b.natoms.tolist())):
+            ref[sid] = p.numpy()
+    parts = np.split(out["pos"], out["chunk_idx"])
+    for sid, p in zip(out["ids"].tolist(), parts):
+        assert np.array_equal(p, ref[sid]), sid
+    files = sorted(os.listdir(tmp_path / "traj"))
+    assert len(files) == 8 and files[0].startswith("0_p0")
+    again = run_diffusion_batches(m, loader, params, device=DEV, traj_dir=tmp_path / "traj", results_dir=None)
+    assert again["ids"].size == 0               # every batch skipped: its trajectories exist
+
+
+def test_single_structure_front_door(sampler_weights):
+    """`run_diffusion(atoms, ...)` (AdsorbDiffCalculator.run_diffusion): duck-typed Atoms in, positions out; float-typed
+    atomic numbers / tags as the ASE converter produces them; 3 placements in one batch."""
+    from adsorbdiff_b200 import run_diffusion
+
+    _reset_sticky_pbc()
+    s = S.make_system(90)
+
+    class Atoms:
+        constraints = []
+        def get_positions(self): return s["pos"]
+        def get_cell(self): return s["cell"]
+        def get_atomic_numbers(self): return s["atomic_numbers"]
+        def get_tags(self): return s["tags"]
+
+    params = dict(num_steps=3, ads_std_low=0.1, ads_std_high=10, rot_std_low=0.01, rot_std_high=1.55, early_stop=False)
+    m = _model(sampler_weights)
+    torch.manual_seed(4)
+    pos = run_diffusion(Atoms(), m, params, device=DEV, placements=3)
+    assert pos.shape == (3, len(s["pos"]), 3)
+    slab = s["tags"] != 2
+    assert np.array_equal(pos[0][slab], s["pos"][slab]) and not np.allclose(pos[0][~slab], pos[1][~slab])
