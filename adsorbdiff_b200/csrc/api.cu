@@ -14,5 +14,6 @@ extern "C" int adk_init(void) {
     if ((rc = adk_linear_tc_set_attrs()) != 0) return rc;
     if ((rc = adk_message_mma_set_attrs()) != 0) return rc;
     if ((rc = adk_message_t5_set_attrs()) != 0) return rc;
+    if ((rc = adk_message_bwd_set_attrs()) != 0) return rc;
     return 0;
 }

@@ -64,3 +64,8 @@ int adk_linear_set_attrs();
 int adk_linear_tc_set_attrs();
 int adk_message_mma_set_attrs();
 int adk_message_t5_set_attrs();
+int adk_message_bwd_set_attrs();
+int adk_message_bwd_nodes(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const float* e_geo,
+                          const float* xh, const float* vec_in, const float* w_rbf, const float* b_rbf,
+                          const float* rbf_offset, int N, int F, int R, float cutoff, int envelope_exponent,
+                          const float* g_dx, const float* g_dvec, float* d_xh, float* d_vec, void* stream);

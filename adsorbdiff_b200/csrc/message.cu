@@ -46,8 +46,17 @@ struct MsParams {
     int env_p;
     float* x_io;
     float* vec_out;
+    // backward w.r.t. the node features (BWD instantiation, see csrc/message_bwd.cu)
+    const float* g_x;   // [N][F]    dL/d dx
+    const float* g_v;   // [N][3][F] dL/d dvec
+    float* d_xh;        // [N][3F]
+    float* d_vec;       // [N][3][F]
 };
 
+// BWD = false: the forward op.  BWD = true: its transpose w.r.t. (xh, vec) -- row t is then the SOURCE atom and the walk
+// over its in-edges visits the mirrors of its out-edges (same distance, negated unit vector), gathering the output
+// gradients of the atom at the other end instead of its features.  Same staging, same tap loop.
+template <bool BWD>
 __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
     extern __shared__ __align__(16) float s_w[];  // [R][3][FS]
     float* s_mu = s_w + (size_t)P.R * 3 * FS;     // [R]
@@ -85,6 +94,15 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
         const int start = P.row_start[t], deg = P.row_deg[t];
         float2 dx = make_float2(0.f, 0.f);
         float2 dv[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        float2 t2 = make_float2(0.f, 0.f), t3 = make_float2(0.f, 0.f);
+        float2 own[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        if constexpr (BWD) {
+            if (has_vec) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    own[c] = *reinterpret_cast<const float2*>(P.vec_in + (size_t)t * 3 * F + c * F + f0 + fl);
+            }
+        }
         // software pipeline: the CSR records of the next group are fetched while this one is processed
         int nx_src = 0;
         float4 nx_geo = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -134,13 +152,20 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
                 rh[j][1] = __shfl_sync(ADK_FULL_MASK, my_geo.z, j);
                 rh[j][2] = __shfl_sync(ADK_FULL_MASK, my_geo.w, j);
                 if (j < cnt) {
-                    const float* xs = P.xh + (size_t)src * 3 * F + f0 + fl;
-#pragma unroll
-                    for (int g = 0; g < 3; ++g) hx[j][g] = *reinterpret_cast<const float2*>(xs + g * F);
-                    if (has_vec) {
-                        const float* vs = P.vec_in + (size_t)src * 3 * F + f0 + fl;
+                    if constexpr (BWD) {
+                        hx[j][0] = *reinterpret_cast<const float2*>(P.g_x + (size_t)src * F + f0 + fl);
+                        const float* vs = P.g_v + (size_t)src * 3 * F + f0 + fl;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) vx[j][c] = *reinterpret_cast<const float2*>(vs + c * F);
+                    } else {
+                        const float* xs = P.xh + (size_t)src * 3 * F + f0 + fl;
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) hx[j][g] = *reinterpret_cast<const float2*>(xs + g * F);
+                        if (has_vec) {
+                            const float* vs = P.vec_in + (size_t)src * 3 * F + f0 + fl;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) vx[j][c] = *reinterpret_cast<const float2*>(vs + c * F);
+                        }
                     }
                 }
             }
@@ -178,6 +203,23 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
             }
 #pragma unroll
             for (int j = 0; j < EG; ++j) {
+                if constexpr (BWD) {
+                    if (j < cnt) {
+                        // t1 += r1 g_x ; t2 += r2 (vec_t . g_v) ; dv += r2 g_v ; t3 += r3 (-rhat . g_v)
+                        dx.x += rb[j][0].x * hx[j][0].x;
+                        dx.y += rb[j][0].y * hx[j][0].y;
+                        float s2x = 0.f, s2y = 0.f, s3x = 0.f, s3y = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            s2x += own[c].x * vx[j][c].x; s2y += own[c].y * vx[j][c].y;
+                            s3x -= rh[j][c] * vx[j][c].x; s3y -= rh[j][c] * vx[j][c].y;
+                            dv[c].x += rb[j][1].x * vx[j][c].x; dv[c].y += rb[j][1].y * vx[j][c].y;
+                        }
+                        t2.x += rb[j][1].x * s2x; t2.y += rb[j][1].y * s2y;
+                        t3.x += rb[j][2].x * s3x; t3.y += rb[j][2].y * s3y;
+                    }
+                    continue;
+                }
                 if (j < cnt) {
                     dx.x += hx[j][0].x * rb[j][0].x;
                     dx.y += hx[j][0].y * rb[j][0].y;
@@ -200,6 +242,19 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
             }
             e0 += cnt;
         }
+        if constexpr (BWD) {
+            const float k2 = inv_sqrt_3 * inv_sqrt_h;
+            float* o = P.d_xh + (size_t)t * 3 * F + f0 + fl;
+            *reinterpret_cast<float2*>(o) = dx;
+            *reinterpret_cast<float2*>(o + F) = make_float2(t2.x * k2, t2.y * k2);
+            *reinterpret_cast<float2*>(o + 2 * F) = make_float2(t3.x * inv_sqrt_h, t3.y * inv_sqrt_h);
+            const float2 x2 = *reinterpret_cast<const float2*>(P.xh + (size_t)t * 3 * F + F + f0 + fl);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                *reinterpret_cast<float2*>(P.d_vec + (size_t)t * 3 * F + c * F + f0 + fl) =
+                    make_float2(x2.x * k2 * dv[c].x, x2.y * k2 * dv[c].y);
+            continue;
+        }
         float2* xo = reinterpret_cast<float2*>(P.x_io + (size_t)t * F + f0 + fl);
         float2 xv = *xo;
         xv.x = (xv.x + dx.x) * 0.70710678118654752440f;
@@ -215,17 +270,9 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
     }
 }
 
-}  // namespace
-
-extern "C" int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
-                           const float* e_geo, const float* xh, const float* vec_in, const float* w_rbf,
-                           const float* b_rbf, const float* rbf_offset, int N, int F, int R, float cutoff,
-                           int envelope_exponent, float* x_io, float* vec_out, void* stream) {
-    if (!row_start || !row_deg || !e_src || !e_geo || !xh || !w_rbf || !b_rbf || !rbf_offset || !x_io ||
-        !vec_out || N <= 0)
-        return ADK_EINVAL;
-    if (F % FS != 0 || R < NTAPS || (R & 3) || envelope_exponent < 1 || vec_in == vec_out) return ADK_EINVAL;
-    MsParams P;
+void fill_params(MsParams& P, const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const float* e_geo,
+                 const float* xh, const float* vec_in, const float* w_rbf, const float* b_rbf, const float* rbf_offset,
+                 int N, int F, int R, float cutoff, int envelope_exponent) {
     P.row_start = row_start; P.row_deg = row_deg; P.e_src = e_src;
     P.e_geo = reinterpret_cast<const float4*>(e_geo);
     P.xh = xh; P.vec_in = vec_in; P.w_rbf = w_rbf; P.b_rbf = b_rbf; P.rbf_offset = rbf_offset;
@@ -238,14 +285,50 @@ extern "C" int adk_message(const int32_t* row_start, const int32_t* row_deg, con
     P.env_a = (float)(-(p + 1) * (p + 2) / 2);
     P.env_b = (float)(p * (p + 2));
     P.env_c = (float)(-p * (p + 1) / 2);
-    P.x_io = x_io; P.vec_out = vec_out;
-    const size_t smem = sizeof(float) * ((size_t)R * 3 * FS + ((R + 3) & ~3)) + sizeof(float4) * 32 * MS_WARPS;
+    P.x_io = nullptr; P.vec_out = nullptr; P.g_x = nullptr; P.g_v = nullptr; P.d_xh = nullptr; P.d_vec = nullptr;
+}
+
+size_t smem_bytes(int R) {
+    return sizeof(float) * ((size_t)R * 3 * FS + ((R + 3) & ~3)) + sizeof(float4) * 32 * MS_WARPS;
+}
+
+}  // namespace
+
+// node-feature half of adk_message_bwd (csrc/message_bwd.cu)
+int adk_message_bwd_nodes(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const float* e_geo,
+                          const float* xh, const float* vec_in, const float* w_rbf, const float* b_rbf,
+                          const float* rbf_offset, int N, int F, int R, float cutoff, int envelope_exponent,
+                          const float* g_dx, const float* g_dvec, float* d_xh, float* d_vec, void* stream) {
+    if (F % FS != 0 || R < NTAPS || (R & 3) || envelope_exponent < 1) return ADK_EINVAL;
+    MsParams P;
+    fill_params(P, row_start, row_deg, e_src, e_geo, xh, vec_in, w_rbf, b_rbf, rbf_offset, N, F, R, cutoff, envelope_exponent);
+    P.g_x = g_dx; P.g_v = g_dvec; P.d_xh = d_xh; P.d_vec = d_vec;
     dim3 grid((N + ROWS_PER_CTA - 1) / ROWS_PER_CTA, F / FS);
-    message_kernel<<<grid, MS_THREADS, smem, adk::as_stream(stream)>>>(P);
+    message_kernel<true><<<grid, MS_THREADS, smem_bytes(R), adk::as_stream(stream)>>>(P);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
+                           const float* e_geo, const float* xh, const float* vec_in, const float* w_rbf,
+                           const float* b_rbf, const float* rbf_offset, int N, int F, int R, float cutoff,
+                           int envelope_exponent, float* x_io, float* vec_out, void* stream) {
+    if (!row_start || !row_deg || !e_src || !e_geo || !xh || !w_rbf || !b_rbf || !rbf_offset || !x_io ||
+        !vec_out || N <= 0)
+        return ADK_EINVAL;
+    if (F % FS != 0 || R < NTAPS || (R & 3) || envelope_exponent < 1 || vec_in == vec_out) return ADK_EINVAL;
+    MsParams P;
+    fill_params(P, row_start, row_deg, e_src, e_geo, xh, vec_in, w_rbf, b_rbf, rbf_offset, N, F, R, cutoff, envelope_exponent);
+    P.x_io = x_io; P.vec_out = vec_out;
+    const size_t smem = smem_bytes(R);
+    dim3 grid((N + ROWS_PER_CTA - 1) / ROWS_PER_CTA, F / FS);
+    message_kernel<false><<<grid, MS_THREADS, smem, adk::as_stream(stream)>>>(P);
     ADK_LAUNCH_CHECK();
     return 0;
 }
 
 int adk_message_set_attrs() {
-    return (int)cudaFuncSetAttribute(message_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    int rc = (int)cudaFuncSetAttribute(message_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    if (rc) return rc;
+    return (int)cudaFuncSetAttribute(message_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
 }

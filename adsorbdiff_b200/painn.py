@@ -12,8 +12,10 @@ The torch modules below only *hold parameters* in the reference's layout; none o
 `forward`s run.  All arithmetic happens in the CUDA kernels reached through the C ABI
 (`_cabi.py`).  There is no CPU / eager fallback: a CPU tensor or a missing library raises.
 
-Scope: inference (sampling) forward, fp32.  The training step (autograd through the
-kernels) is row f-1 of SURVEY.md section 8 and raises NotImplementedError here.
+Scope: the inference (sampling) forward, fp32, on the kernels.  In training mode with autograd
+enabled `forward` routes to `train.forward_train`: the same graph
+kernel, the message op as an autograd Function over hand-written forward/backward kernels, the
+node-wise layers as torch ops.
 """
 from __future__ import annotations
 
@@ -744,12 +746,6 @@ class PaiNN(nn.Module):
         for k in range(2 if self.so3_denoising else 1):
             call("adk_scatter_rows", dev, ptr(q.out[k]), ptr(idx), ns, 3, ptr(p.out[k]))
 
-    def _refuse_training(self) -> None:
-        if torch.is_grad_enabled() and self.training:
-            raise NotImplementedError(
-                "adsorbdiff_b200.PaiNN implements the sampling (inference) forward; the training step "
-                "(autograd through the kernels) is not built yet -- call under torch.no_grad()/eval()")
-
     def _prepare(self, data):
         p = self.plan(data)
         if self.atom_emb.embeddings.weight.device != p.device:
@@ -819,7 +815,10 @@ class PaiNN(nn.Module):
         return self.auto_calibrate and self._scales is None and self._calib is None and (self.gemm == "tc" or self.msg == "t5")
 
     def forward(self, data, trace: Optional[dict] = None):
-        self._refuse_training()
+        if torch.is_grad_enabled() and self.training:
+            # training step: differentiable forward, see train.py
+            from .train import forward_train
+            return forward_train(self, data)
         with torch.no_grad():
             if self._needs_calibration():
                 self.calibrate(data)

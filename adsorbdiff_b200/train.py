@@ -1,0 +1,366 @@
+"""Training step of the score model.
+
+Reference: adsorbdiff/trainers/sde_denoising_trainer.py -- `tr_so3_schedule` (:67-135, noising of a batch),
+`_forward_denoising` (:539-553), `_compute_loss` (:675-728), the loop body of `train` (:409-447) and
+`BaseTrainer._backward` (base_trainer.py:787-820: zero_grad, backward, clip, step, EMA); IGSO(3) tables
+adsorbdiff/utils/rot_utils.py:142-264.
+
+What runs where:
+  * the radius graph is the sampler's own kernel (csrc/neighbors.cu) -- with `direct_forces` nothing
+    differentiates through positions, so the graph is data;
+  * the message op (edge featurisation + rbf projection + message + aggregation, the part of PaiNN that is not a
+    plain GEMM) is a `torch.autograd.Function` over two hand-written kernels: forward csrc/message.cu (exact fp32),
+    backward csrc/message_bwd.cu -- no per-edge tensor ever exists in HBM, where the reference's autograd keeps
+    rbf [E,128], rbf_proj(rbf) [E,1536] and the messages [E,3,512] alive per layer (about 3.5 GB per layer at 48
+    systems);
+  * LayerNorm, the Linear layers (cuBLAS fp32), SiLU and the gated blocks are plain torch ops under autograd:
+    library GEMMs, fp32 like the reference's default (no AMP);
+  * the noising schedule is vectorised on the device (the reference loops over systems on the host with numpy
+    RNG and scipy-free table lookups, :104-125); same distributions, different random stream.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import _cabi
+from ._cabi import call, ptr
+
+INV_SQRT_2 = 1.0 / math.sqrt(2.0)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# message op under autograd
+# --------------------------------------------------------------------------------------------------------------
+class MessageFn(torch.autograd.Function):
+    """(x, vec, xh, W_rbf, b_rbf) -> ((x + dx) / sqrt(2), vec + dvec); PaiNNMessage + residual
+    (painn_denoising.py:443-445, 534-567).  `vec` may be None (first layer)."""
+
+    @staticmethod
+    def forward(ctx, x, vec, xh, w, b, net, p):
+        N, F_, R = p.N, net.hidden_channels, net.num_rbf
+        x_out = x.detach().clone().contiguous()
+        vec_in = vec.detach().contiguous() if vec is not None else None
+        vec_out = torch.empty(N, 3, F_, dtype=torch.float32, device=x.device)
+        xh_c, w_c, b_c = xh.detach().contiguous(), w.detach().contiguous(), b.detach().contiguous()
+        call("adk_message", p.device, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(xh_c),
+             ptr(vec_in), ptr(w_c), ptr(b_c), ptr(net.radial_basis.rbf.offset), N, F_, R, float(net.cutoff),
+             net.radial_basis.exponent, ptr(x_out), ptr(vec_out))
+        ctx.net, ctx.p, ctx.has_vec = net, p, vec is not None
+        ctx.save_for_backward(xh_c, vec_in if vec_in is not None else xh_c.new_empty(0), w_c, b_c)
+        return x_out, vec_out
+
+    @staticmethod
+    def backward(ctx, g_x, g_vec):
+        net, p = ctx.net, ctx.p
+        xh, vec_in, w, b = ctx.saved_tensors
+        N, F_, R = p.N, net.hidden_channels, net.num_rbf
+        dev = p.device
+        g_dx = (g_x * INV_SQRT_2).contiguous()
+        g_dvec = g_vec.contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_xh = torch.empty(N, 3 * F_, **f32)
+        d_vec = torch.empty(N, 3, F_, **f32)
+        d_w = torch.empty(3 * F_, R, **f32)
+        d_b = torch.empty(3 * F_, **f32)
+        n_scratch = _cabi.load().adk_message_bwd_scratch_floats(N, F_, R, None)
+        scratch = torch.empty(n_scratch, **f32)
+        call("adk_message_bwd", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(xh),
+             ptr(vec_in) if ctx.has_vec else None, ptr(w), ptr(b), ptr(net.radial_basis.rbf.offset), N, F_, R,
+             float(net.cutoff), net.radial_basis.exponent, ptr(g_dx), ptr(g_dvec), ptr(d_xh), ptr(d_vec), ptr(d_w),
+             ptr(d_b), ptr(scratch))
+        grad_vec = (g_dvec + d_vec) if ctx.has_vec else None
+        return g_dx, grad_vec, d_xh, d_w, d_b, None, None
+
+
+def _ssilu(x):
+    """ScaledSiLU (gemnet_oc/layers/base_layers.py:65-72)"""
+    return F.silu(x) * (1.0 / 0.6)
+
+
+def _mlp(seq, x):
+    return seq[2](_ssilu(seq[0](x)))
+
+
+def _gated_block(blk, x, v, out_channels: int):
+    """GatedEquivariantBlock.forward (painn_denoising.py:688-697)"""
+    vec1 = torch.norm(blk.vec1_proj(v), dim=-2)
+    vec2 = blk.vec2_proj(v)
+    h = _mlp(blk.update_net, torch.cat([x, vec1], dim=-1))
+    xo, g = torch.split(h, out_channels, dim=-1)
+    return _ssilu(xo), g.unsqueeze(1) * vec2
+
+
+def forward_train(net, data, check: bool = True):
+    """The differentiable forward of `adsorbdiff_b200.PaiNN` (PaiNN.forward, painn_denoising.py:402-481).  Returns
+    forces [N,3] (and forces2 with `so3_denoising`) attached to the autograd graph of the parameters.  `check` reads
+    the device status word (empty system, bad element, row overflow) before returning -- one host sync; `TrainStep`
+    defers it until the backward pass has been enqueued."""
+    p, z, pos = net._prepare(data)
+    net._graph(p, pos)
+    F_ = net.hidden_channels
+    x = net.atom_emb.embeddings(z - 1)
+    vec = None
+    for l in range(net.num_layers):
+        m, u = net.message_layers[l], net.update_layers[l]
+        xh = _mlp(m.x_proj, m.x_layernorm(x))
+        x, vec = MessageFn.apply(x, vec, xh, m.rbf_proj.weight, m.rbf_proj.bias, net, p)
+        v1, v2 = torch.split(u.vec_proj(vec), F_, dim=-1)
+        vec_dot = (v1 * v2).sum(dim=1) * (1.0 / math.sqrt(F_))
+        h = _mlp(u.xvec_proj, torch.cat([x, torch.sqrt(torch.sum(v2 ** 2, dim=-2) + 1e-8)], dim=-1))
+        a, bq, c = torch.split(h, F_, dim=-1)
+        x = x + (a + bq * vec_dot) * INV_SQRT_2
+        vec = vec + c.unsqueeze(1) * v1
+        sc = getattr(net, "upd_out_scalar_scale_%d" % l).scale_factor
+        x = torch.where(sc != 0.0, x * sc, x)   # ScaleFactor.forward multiplies only when fitted (no host sync here)
+    outs = []
+    for head in ([net.out_forces, net.out_forces2] if net.so3_denoising else [net.out_forces]):
+        hx, hv = _gated_block(head.output_network[0], x, vec, F_ // 2)
+        hx, hv = _gated_block(head.output_network[1], hx, hv, 1)
+        outs.append(hv.squeeze(-1))
+    net._train_plan = p
+    if check:
+        net.check_status(p)
+    return outs[0] if not net.so3_denoising else tuple(outs)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# IGSO(3) tables (rot_utils.py:9-10, 142-215)
+# --------------------------------------------------------------------------------------------------------------
+class IGSO3Tables:
+    """cdf / score-norm tables of the isotropic Gaussian on SO(3), built once on `device` in float64 by the series
+    the reference sums on the host (:151-160 `_expansion`, :174-188 `_score`, :205-215) -- about a second on a GPU
+    at the reference's sizes (N_EPS=1000, X_N=2000, L=2000) against minutes of numpy.  Lookups reproduce the
+    reference's index arithmetic, including `* N_EPS` (not N_EPS - 1) before rounding (:226-231)."""
+
+    def __init__(self, device="cpu", min_eps=0.01, max_eps=2.0, n_eps=1000, x_n=2000, L=2000):
+        self.min_eps, self.max_eps, self.n_eps, self.x_n = float(min_eps), float(max_eps), int(n_eps), int(x_n)
+        dev = torch.device(device)
+        f64 = dict(dtype=torch.float64, device=dev)
+        eps = 10 ** torch.linspace(math.log10(min_eps), math.log10(max_eps), n_eps, **f64)
+        om = torch.linspace(0, math.pi, x_n + 1, **f64)[1:]
+        l = torch.arange(L, **f64)
+        lo = torch.sin(om / 2)                                  # [X]
+        dlo = 0.5 * torch.cos(om / 2)
+        hi = torch.sin(om[:, None] * (l[None, :] + 0.5))        # [X, L]
+        dhi = (l[None, :] + 0.5) * torch.cos(om[:, None] * (l[None, :] + 0.5))
+        term_e = hi / lo[:, None]
+        term_s = (lo[:, None] * dhi - hi * dlo[:, None]) / (lo[:, None] ** 2)
+        wgt = (2 * l[None, :] + 1) * torch.exp(-l[None, :] * (l[None, :] + 1) * eps[:, None] ** 2)   # [n_eps, L]
+        exp_vals, dsig = wgt @ term_e.T, wgt @ term_s.T                                                  # [n_eps, X]
+        pdf = exp_vals * (1 - torch.cos(om))[None, :] / math.pi
+        self.omegas = om
+        self.cdf = pdf.cumsum(dim=1) / x_n * math.pi
+        self.score_norms = dsig / exp_vals
+        self.exp_score_norms = torch.sqrt((self.score_norms ** 2 * pdf).sum(1) / pdf.sum(1) / math.pi)
+
+    def to(self, device):
+        for k in ("omegas", "cdf", "score_norms", "exp_score_norms"):
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
+    def eps_index(self, eps: torch.Tensor) -> torch.Tensor:
+        idx = (torch.log10(eps.double()) - math.log10(self.min_eps)) / (math.log10(self.max_eps) - math.log10(self.min_eps)) * self.n_eps
+        return torch.clamp(torch.round(idx).long(), 0, self.n_eps - 1)
+
+    @staticmethod
+    def _interp(x, xp, fp):
+        """np.interp row-wise: x [B], xp [B, X] increasing, fp [B, X] (clamped at the ends)."""
+        X = xp.shape[1]
+        hi = torch.searchsorted(xp.contiguous(), x[:, None].contiguous(), right=True).squeeze(1)
+        lo_i = torch.clamp(hi - 1, 0, X - 1)
+        hi_i = torch.clamp(hi, 0, X - 1)
+        x0, x1 = xp.gather(1, lo_i[:, None]).squeeze(1), xp.gather(1, hi_i[:, None]).squeeze(1)
+        f0, f1 = fp.gather(1, lo_i[:, None]).squeeze(1), fp.gather(1, hi_i[:, None]).squeeze(1)
+        w = torch.where(x1 > x0, (x - x0) / torch.where(x1 > x0, x1 - x0, torch.ones_like(x0)), torch.zeros_like(x0))
+        out = f0 + w * (f1 - f0)
+        out = torch.where(x <= xp[:, 0], fp[:, 0], out)
+        return torch.where(x >= xp[:, -1], fp[:, -1], out)
+
+    def sample_vec(self, eps: torch.Tensor, generator=None, axis=None, u=None) -> torch.Tensor:
+        """`sample_vec` (:236-239) for a vector of eps: uniform axis, angle by inverse-cdf lookup.  float64 [B,3].
+        `axis` [B,3] (unnormalised normal draws) and `u` [B] (uniform draws) may be supplied (tests)."""
+        B, dev = eps.shape[0], self.cdf.device
+        idx = self.eps_index(eps)
+        if axis is None:
+            axis = torch.randn(B, 3, dtype=torch.float64, device=dev, generator=generator)
+        axis = axis / axis.norm(dim=1, keepdim=True)
+        if u is None:
+            u = torch.rand(B, dtype=torch.float64, device=dev, generator=generator)
+        omega = self._interp(u, self.cdf[idx], self.omegas[None, :].expand(B, -1))
+        return axis * omega[:, None]
+
+    def score_vec(self, eps: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
+        """`score_vec` (:242-251): interp(|vec|, omegas, score_norms[eps]) * vec / |vec|."""
+        idx = self.eps_index(eps)
+        om = vec.norm(dim=1)
+        B = vec.shape[0]
+        s = self._interp(om, self.omegas[None, :].expand(B, -1), self.score_norms[idx])
+        return s[:, None] * vec / om[:, None]
+
+    def score_norm(self, eps: torch.Tensor) -> torch.Tensor:
+        """`score_norm` (:254-262), float32 with the shape of `eps`."""
+        return self.exp_score_norms[self.eps_index(eps)].float()
+
+
+def axis_angle_to_matrix(aa: torch.Tensor) -> torch.Tensor:
+    """rot_utils.py:18-98 (axis-angle -> quaternion -> matrix) for [B,3]."""
+    angle = aa.norm(dim=1, keepdim=True)
+    half = 0.5 * angle
+    small = angle.abs() < 1e-6
+    k = torch.where(small, 0.5 - angle * angle / 48, torch.sin(half) / torch.where(small, torch.ones_like(angle), angle))
+    q = torch.cat([torch.cos(half), aa * k], dim=1)
+    r, i, j, kq = q.unbind(1)
+    two_s = 2.0 / (q * q).sum(1)
+    return torch.stack([
+        1 - two_s * (j * j + kq * kq), two_s * (i * j - kq * r), two_s * (i * kq + j * r),
+        two_s * (i * j + kq * r), 1 - two_s * (i * i + kq * kq), two_s * (j * kq - i * r),
+        two_s * (i * kq - j * r), two_s * (j * kq + i * r), 1 - two_s * (i * i + j * j)], dim=1).reshape(-1, 3, 3)
+
+
+def _segment_mean(values, seg, B):
+    out = torch.zeros(B, values.shape[1], dtype=values.dtype, device=values.device).index_add_(0, seg, values)
+    cnt = torch.zeros(B, dtype=values.dtype, device=values.device).index_add_(0, seg, torch.ones_like(seg, dtype=values.dtype))
+    return out / cnt.clamp_min(1)[:, None]
+
+
+@torch.no_grad()
+def pbc_correction(noise_vec, cell):
+    """Minimum-image wrap of a per-system vector (sde_denoising_trainer.py:45-64): fractional coordinates mod 1,
+    mapped to (-0.5, 0.5]."""
+    frac = torch.linalg.solve(cell.double().transpose(1, 2), noise_vec.double()[:, :, None]).squeeze(2)
+    frac = frac % 1.0
+    frac = frac % 1.0
+    frac = torch.where(frac > 0.5, frac - 1, frac)
+    return torch.einsum("bi,bij->bj", frac.float(), cell.float())
+
+
+@torch.no_grad()
+def tr_so3_schedule(batch, params: dict, tables: IGSO3Tables, generator=None, draws: Optional[dict] = None):
+    """Noise a batch for one training step (sde_denoising_trainer.py:67-135), all systems at once on the device:
+    t ~ U(0,1) per system, sigma = low^(1-t) high^t, xy-translation of the adsorbate by N(0, sigma_tr^2) wrapped to
+    the minimum image, a rotation about the adsorbate's centre drawn from IGSO(3)(sigma_rot), +1 A in z.  Sets
+    `tr_sigma`, `rot_sigma`, `rot_score`, `tr_score`, `ads_center_noise_vec` and rewrites `batch.pos[tags == 2]`.
+    `draws` = dict(t [B], normal [B,3], axis [B,3], u [B]) replaces the random draws (parity tests)."""
+    dev = batch.pos.device
+    B = int(batch.natoms.shape[0])
+    d = draws or {}
+    t = d["t"] if "t" in d else torch.rand(B, device=dev, generator=generator)
+    tr_sigma = params["ads_std_low"] ** (1 - t) * params["ads_std_high"] ** t
+    rot_sigma = params["rot_std_low"] ** (1 - t) * params["rot_std_high"] ** t
+    ads = batch.tags == 2
+    seg = batch.batch[ads]
+    ads_pos = batch.pos[ads]
+    center = _segment_mean(ads_pos, seg, B)
+    noise = (d["normal"] if "normal" in d else torch.randn(B, 3, device=dev, generator=generator)) * tr_sigma[:, None]
+    noise = pbc_correction(noise, batch.cell.reshape(B, 3, 3))
+    noise[:, -1] = 0
+    rot_update = tables.sample_vec(rot_sigma, generator, d.get("axis"), d.get("u"))   # float64 like the numpy original
+    rot_mat = axis_angle_to_matrix(rot_update).float()
+    rot_score = tables.score_vec(rot_sigma, rot_update).float()
+    rel = ads_pos - center[seg]
+    new_pos = torch.einsum("nj,nij->ni", rel, rot_mat[seg]) + noise[seg] + center[seg]   # rel @ R^T
+    new_pos[:, -1] += 1
+    batch.tr_sigma, batch.rot_sigma = tr_sigma[:, None], rot_sigma[:, None]
+    batch.rot_score = rot_score
+    pos = batch.pos.clone()
+    pos[ads] = new_pos
+    batch.pos = pos
+    batch.ads_center_noise_vec = noise
+    batch.tr_score = -noise / tr_sigma[:, None] ** 2
+    return batch
+
+
+def denoising_loss(out, batch, tables: Optional[IGSO3Tables], denoising_pos_coefficient: float = 1.0):
+    """`DenoisingTrainer._compute_loss` (:675-728): adsorbate-mean of the two heads, divided by sigma; translation
+    term weighted by sigma^2 with z zeroed, rotation term divided by the expected score norm; both `.mean()`s are
+    over [B, 3].  (`denoising_pos_coefficient` is read and never applied by the reference, :680-682 -- same here.)"""
+    so3 = isinstance(out, (tuple, list))
+    tr_out = out[0] if so3 else out
+    ads = batch.tags == 2
+    seg = batch.batch[ads]
+    B = int(batch.natoms.shape[0])
+    tr = _segment_mean(tr_out[ads], seg, B) / batch.tr_sigma
+    zmask = torch.tensor([1.0, 1.0, 0.0], device=tr.device)
+    tr = tr * zmask
+    loss = ((tr - batch.tr_score) ** 2 * batch.tr_sigma ** 2).mean()
+    if so3:
+        rot = _segment_mean(out[1][ads], seg, B) / batch.rot_sigma
+        norm = tables.score_norm(batch.rot_sigma)
+        loss = loss + (((rot - batch.rot_score) / norm) ** 2).mean()
+    return loss
+
+
+# --------------------------------------------------------------------------------------------------------------
+# one optimisation step
+# --------------------------------------------------------------------------------------------------------------
+def allreduce_mean_(tensors) -> None:
+    """Average `tensors` over the ranks in place with ONE all-reduce of a flat buffer (what DistributedDataParallel
+    does bucket by bucket for the gradients; the whole model is 42 MB, one bucket)."""
+    world = dist.get_world_size()
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat)
+    flat.div_(world)
+    o = 0
+    for t in tensors:
+        t.copy_(flat[o:o + t.numel()].view_as(t))
+        o += t.numel()
+
+
+class TrainStep:
+    """noise -> forward -> loss -> backward -> (all-reduce) -> clip -> AdamW -> EMA; the body of
+    `DenoisingTrainer.train` (:409-447) + `_backward` (base_trainer.py:787-820) with the optimizer set up as
+    `load_optimizer` does (:556-612: no weight decay on embeddings and biases).
+
+    Data parallel: one process per GPU, each on its own batch; gradients are averaged with ONE all-reduce of a flat
+    fp32 buffer (10.6 M parameters = 42 MB) over NCCL -- DistributedDataParallel's average (world-size mean) without
+    its per-bucket hooks."""
+
+    def __init__(self, net, optim: dict, tables: Optional[IGSO3Tables] = None, generator=None):
+        self.net, self.optim, self.generator = net, optim, generator
+        self.params = [q for q in net.parameters() if q.requires_grad]
+        dev = self.params[0].device
+        self.tables = tables if tables is not None else (IGSO3Tables(dev) if net.so3_denoising else None)
+        wd = float(optim.get("optimizer_params", {}).get("weight_decay", 0))
+        skip = set(net.no_weight_decay())
+        no_decay = [q for n, q in net.named_parameters() if q.requires_grad and n in skip]
+        decay = [q for n, q in net.named_parameters() if q.requires_grad and n not in skip]
+        groups = [{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": wd}]
+        name = optim.get("optimizer", "AdamW")
+        if name != "AdamW":
+            raise NotImplementedError("the denoising configs train with AdamW")
+        self.optimizer = torch.optim.AdamW(groups, lr=float(optim.get("lr_initial", 1e-4)), fused=dev.type == "cuda")
+        self.clip = optim.get("clip_grad_norm")
+        self.ema_decay = optim.get("ema_decay")
+        self.shadow = [q.detach().clone() for q in self.params] if self.ema_decay else None
+        self.pos_params = optim.get("denoising_pos_params", {})
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.step_count = 0
+
+    def __call__(self, batch, noised: bool = False) -> torch.Tensor:
+        net = self.net
+        net.train()
+        if not noised:
+            if net.so3_denoising:
+                batch = tr_so3_schedule(batch, self.pos_params, self.tables, self.generator)
+            else:
+                raise NotImplementedError("ads_COM_gaussian_schedule (so3_denoising=False) is not built")
+        out = forward_train(net, batch, check=False)
+        loss = denoising_loss(out, batch, self.tables)
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        net.check_status(net._train_plan)   # raises before the optimizer sees gradients of a malformed batch
+        if self.world > 1:
+            allreduce_mean_([q.grad for q in self.params if q.grad is not None])
+        if self.clip:
+            torch.nn.utils.clip_grad_norm_(self.params, max_norm=float(self.clip), foreach=True)
+        self.optimizer.step()
+        if self.shadow is not None:   # ExponentialMovingAverage.update (exponential_moving_average.py:71-97)
+            torch._foreach_lerp_(self.shadow, [q.detach() for q in self.params], 1.0 - float(self.ema_decay))
+        self.step_count += 1
+        return loss.detach()

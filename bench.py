@@ -589,6 +589,137 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- training step
+TRAIN_OPTIM = dict(   # configs/denoising/painn_so3.yml:56-87
+    optimizer="AdamW", optimizer_params=dict(weight_decay=0.001), lr_initial=1e-4, clip_grad_norm=100, ema_decay=0.999,
+    denoising_pos_params=dict(num_steps=100, ads_std_low=0.1, ads_std_high=10, rot_std_low=0.01, rot_std_high=1.55,
+                              free_std_low=0.01, free_std_high=0.1))
+TRAIN_BATCH = 48      # systems per GPU (optim.batch_size of the same file)
+
+
+def reference_train_rate(batch, steps, warmup, device):
+    """systems/s of the reference's model code (PaiNN from baseline/_ref, its torch ops + torch autograd) doing the
+    same optimisation step on `device`: forward, loss, backward, clip, AdamW, EMA.  The trainer class cannot be
+    imported without the dataset/registry stack, so noising and the loss are this repo's torch restatement of them
+    (adsorbdiff_b200.train) -- they are a negligible share of the step on either side."""
+    import logging
+
+    from adsorbdiff_b200 import synthetic as S, train as T
+    from oracle import ref_import
+
+    logging.disable(logging.INFO)
+    ns = ref_import.load()
+    model = ns.PaiNN(None, 0, 1, scale_file=ns.scale_file, so3_denoising=True)
+    model.load_state_dict(S.random_state_dict(0), strict=True)
+    model = model.to(device).train()
+    ns.utils.radius_graph_pbc.__defaults__[-1][:] = [True, True, True]
+    params = [q for q in model.parameters() if q.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.001)
+    shadow = [q.detach().clone() for q in params]
+    tables = T.IGSO3Tables(device)
+    t0 = None
+    for i in range(steps + warmup):
+        if i == warmup:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        nb = T.tr_so3_schedule(batch.clone().to(device), TRAIN_OPTIM["denoising_pos_params"], tables)
+        out = model(nb)
+        loss = T.denoising_loss(out, nb, tables)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, max_norm=100)
+        opt.step()
+        torch._foreach_lerp_(shadow, [q.detach() for q in params], 1e-3)
+        float(loss)
+    torch.cuda.synchronize()
+    return batch.num_graphs * steps / (time.perf_counter() - t0)
+
+
+def run_train(args):
+    """`python bench.py --train`: the optimisation step of SURVEY.md section 8 row f-1 at the reference's batch size
+    (48 systems per GPU, weak scaling: data parallel, one gradient all-reduce per step).  A step = noising
+    (tr_so3_schedule) + forward + loss + backward + all-reduce + clip + AdamW + EMA, on a batch copied from pinned
+    host memory inside the timed region, loss read back every step (the reference logs `loss.item()` every step)."""
+    import torch.distributed as dist
+
+    from adsorbdiff_b200 import PaiNN, synthetic as S, train as T
+    from adsorbdiff_b200 import _cabi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.train_batch
+    net = PaiNN(None, 0, 1, so3_denoising=True).to(dev)
+    net.load_state_dict(S.random_state_dict(0), strict=True)
+    step = T.TrainStep(net, TRAIN_OPTIM, T.IGSO3Tables(dev), generator=torch.Generator(device=dev).manual_seed(rank))
+    # a few different pinned host batches, cycled (every step sees a batch structure it has not just seen)
+    hosts = []
+    for k in range(4):
+        h = S.collate([S.make_system((rank * 4 + k) * B + i) for i in range(B)])
+        for name, v in list(h.__dict__.items()):
+            if isinstance(v, torch.Tensor):
+                setattr(h, name, v.pin_memory())
+        hosts.append(h)
+    h2d = sum(v.numel() * v.element_size() for v in hosts[0].__dict__.values() if isinstance(v, torch.Tensor))
+    losses = []
+
+    def one(i):
+        losses.append(float(step(hosts[i % len(hosts)].to(dev, non_blocking=True))))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        one(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _cabi.launch_count
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    launches = (_cabi.launch_count - launches0) // args.steps
+    mem = torch.cuda.max_memory_allocated(dev) / 2**30
+    ref = None
+    if rank == 0 and not args.quick:
+        try:
+            ref_b = min(B, args.train_ref_batch)
+            ref_rate = reference_train_rate(S.collate([S.make_system(i) for i in range(ref_b)]), 3, 2, str(dev))
+            ref = {"value": ref_rate, "unit": "systems/s", "batch": ref_b,
+                   "what": "reference PaiNN module (its torch ops, torch autograd) on this GPU, same step"}
+        except Exception as e:
+            ref = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "train_systems_per_s", "value": world * B * args.steps / (ms / 1e3), "unit": "systems/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"painn_so3 training step, {B} systems/GPU (configs/denoising/painn_so3.yml), "
+                                   "AdamW + clip + EMA, noising included", "l2": "a different batch every step"},
+            "e2e": {"value": world * B * args.steps / (ms / 1e3), "unit": "systems/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "peak_mem_gib": mem, "loss_first_last": [losses[0], losses[-1]],
+            "reference_gpu": ref, "clocks": clocks,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -597,8 +728,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--systems", type=int, default=1024, help="systems in the whole job (split over the ranks)")
     ap.add_argument("--quick", action="store_true", help="skip the secondary legs (weak, e2e full_forward, reference_gpu)")
+    ap.add_argument("--train", action="store_true", help="time the training step (row f-1) instead of the sampler")
+    ap.add_argument("--train-batch", type=int, default=TRAIN_BATCH, help="systems per GPU for --train")
+    ap.add_argument("--train-ref-batch", type=int, default=TRAIN_BATCH, help="batch of the reference_gpu leg of --train")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.train:
+        run_train(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -204,6 +204,22 @@ int adk_message_t5(const int32_t* atom_off, int B, int n_max,
                    void* vec_split /* fp16 [2][split_rows][F], row = atom*3+xyz, or NULL */, int64_t split_rows,
                    float split_scale, uint32_t* status, void* stream);
 
+/*
+ * Backward of the message op for the training step (csrc/message_bwd.cu; the reference differentiates
+ * PaiNNMessage.message/aggregate with torch autograd, painn_denoising.py:534-567).  With g_dx[N][F] = dL/d dx and
+ * g_dvec[N][3][F] = dL/d dvec (dx, dvec as defined for adk_message, before the residual / comp):
+ *   d_xh[N][3F], d_vec[N][3][F] (message part only), d_w[3F][R], d_b[3F].
+ * Uses the symmetry of the edge list (every edge has a mirror of equal length and negated unit vector), so the
+ * transposed aggregation is a walk over the same in-edge CSR.  Exact fp32, deterministic.  F % 128 == 0.
+ * scratch: adk_message_bwd_scratch_floats(N, F, R, NULL) floats.  vec_in may be NULL (first layer: vec == 0).
+ */
+int64_t adk_message_bwd_scratch_floats(int N, int F, int R, int* chunks_out /* may be NULL */);
+int adk_message_bwd(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const float* e_geo,
+                    const float* xh, const float* vec_in, const float* w_rbf, const float* b_rbf,
+                    const float* rbf_offset, int N, int F, int R, float cutoff, int envelope_exponent,
+                    const float* g_dx, const float* g_dvec, float* d_xh, float* d_vec, float* d_w, float* d_b,
+                    float* scratch, void* stream);
+
 /* From vp[N][3][2F] = vec_proj(vec) = (vec1|vec2): dot[N][F] = sum_xyz vec1*vec2 / sqrt(F),
  * cat[N][2F] = [x | sqrt(sum_xyz vec2^2 + 1e-8)].  PaiNNUpdate.forward (painn_denoising.py:602-613). */
 int adk_update_prep(const float* x, const float* vp, int N, int F, float* dot, float* cat /* may be NULL */,

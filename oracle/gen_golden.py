@@ -123,6 +123,7 @@ def main():
               f"|f1|max={float(f1.abs().max()):.4g}")
 
     sampler_goldens(ns, model)
+    training_goldens(ns)
 
 
 def run_reference_sampler(ns, model, b, params, seed):
@@ -181,14 +182,120 @@ def sampler_goldens(ns, model, only=None):
         print(f"{name}: steps {n_run}, final pos checksum {float(b.pos.double().sum()):.6f}")
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# training side: IGSO(3) tables, noising schedule, loss
+# ---------------------------------------------------------------------------------------------------------------
+TRAIN_PARAMS = dict(num_steps=100, ads_std_low=0.1, ads_std_high=10, rot_std_low=0.01, rot_std_high=1.55,
+                    free_std_low=0.01, free_std_high=0.1)
+TABLE_ROWS = (0, 137, 500, 863, 999)   # eps rows of the IGSO(3) tables kept in the fixture
+
+
+def _reference_functions(names):
+    """Compile the named top-level functions / methods of the reference's trainer module from the text where it lies
+    (the module itself cannot be imported: it pulls in lmdb, wandb, the dataset and registry stack).  Nothing is
+    copied into the repo; the functions run once, here, to make the fixtures."""
+    import ast
+
+    import torch_scatter  # the shim
+    rot_utils = sys.modules["adsorbdiff.utils.rot_utils"]
+    path = os.path.join(ref_import.REF_ROOT, "adsorbdiff", "trainers", "sde_denoising_trainer.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    env = dict(torch=torch, np=np, scatter=torch_scatter.scatter, rot_utils=rot_utils)
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in found:
+            mod = ast.Module(body=[node], type_ignores=[])
+            exec(compile(mod, path, "exec"), env)
+            found[node.name] = env[node.name]
+    assert set(found) == set(names), set(names) - set(found)
+    return found, rot_utils
+
+
+def training_goldens(ns):
+    import time
+
+    fns, rot_utils = _reference_functions(["pbc_correction", "tr_so3_schedule", "_compute_loss"])
+    # the reference's own series code (rot_utils.py:151-188), all 1000 eps: this is what its import does on a
+    # machine that has no cache yet (:196-215)
+    t0 = time.time()
+    eps_array = 10 ** np.linspace(np.log10(rot_utils.MIN_EPS), np.log10(rot_utils.MAX_EPS), rot_utils.N_EPS)
+    omegas = np.linspace(0, np.pi, rot_utils.X_N + 1)[1:]
+    exp_vals = np.asarray([rot_utils._expansion(omegas, e) for e in eps_array])
+    pdf_vals = np.asarray([rot_utils._density(e, omegas, marginal=True) for e in exp_vals])
+    cdf_vals = np.asarray([p.cumsum() / rot_utils.X_N * np.pi for p in pdf_vals])
+    score_norms = np.asarray([rot_utils._score(exp_vals[i], omegas, eps_array[i]) for i in range(len(eps_array))])
+    exp_score_norms = np.sqrt(np.sum(score_norms**2 * pdf_vals, axis=1) / np.sum(pdf_vals, axis=1) / np.pi)
+    rot_utils._omegas_array, rot_utils._cdf_vals = omegas, cdf_vals
+    rot_utils._score_norms, rot_utils._exp_score_norms = score_norms, exp_score_norms
+    print(f"reference IGSO(3) tables: {time.time() - t0:.0f} s")
+    rows = np.array(TABLE_ROWS)
+    rec = dict(rows=rows, cdf=cdf_vals[rows], score_norms=score_norms[rows], exp_score_norms=exp_score_norms)
+    # lookups through the reference's own sample / score_vec / score_norm
+    probe_eps = np.array([0.01, 0.0123, 0.05, 0.3, 0.77, 1.55, 2.0, 3.0])
+    np.random.seed(7)
+    draws_u, samp, svec = [], [], []
+    state = np.random.get_state()
+    for e in probe_eps:
+        samp.append(rot_utils.sample(e))
+    np.random.set_state(state)
+    for e in probe_eps:
+        draws_u.append(np.random.rand())
+    vecs = np.random.RandomState(3).randn(len(probe_eps), 3) * np.array([0.01, 0.1, 0.5, 1, 1.5, 2, 2.5, 3.0])[:, None] / 2
+    for e, v in zip(probe_eps, vecs):
+        svec.append(rot_utils.score_vec(eps=e, vec=v))
+    rec.update(probe_eps=probe_eps, probe_u=np.array(draws_u), probe_sample=np.array(samp), probe_vecs=vecs,
+               probe_score_vec=np.array(svec), probe_score_norm=rot_utils.score_norm(torch.tensor(probe_eps)).numpy())
+    np.savez_compressed(os.path.join(OUT, "igso3.npz"), **rec)
+
+    # noising schedule on the jit2 batch (2 systems) and a 3-system mixed batch
+    from tests.cases import CASES
+    for case, seed in (("jit2", 11), ("mixed", 12)):
+        b = CASES[case][0]()
+        pos0 = b.pos.clone()
+        B = b.num_graphs
+        torch.manual_seed(seed)
+        t = torch.rand(B)
+        normal = torch.zeros(B, 3).normal_()
+        np.random.seed(seed)
+        axis, u = [], []
+        for _ in range(B):
+            axis.append(np.random.randn(3))
+            u.append(np.random.rand())
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        nb = fns["tr_so3_schedule"](b, dict(TRAIN_PARAMS))
+        assert torch.equal(pos0[b.tags != 2], nb.pos[b.tags != 2])
+        # loss on seeded stand-ins for the two heads (differentiated)
+        g = torch.Generator().manual_seed(seed + 100)
+        out1 = torch.randn(b.pos.shape[0], 3, generator=g).requires_grad_()
+        out2 = torch.randn(b.pos.shape[0], 3, generator=g).requires_grad_()
+        fake = type("T", (), {})()
+        fake.config = {"optim": {}, "model_attributes": {"so3_denoising": True}}
+        fake.device = "cpu"
+        out = {"positions": out1 * 1.0, "positions_free": out2 * 1.0}
+        loss = fns["_compute_loss"](fake, out, nb)
+        loss.backward()
+        np.savez_compressed(
+            os.path.join(OUT, f"train_{case}.npz"), seed=np.array(seed), t=t.numpy(), normal=normal.numpy(),
+            axis=np.array(axis), u=np.array(u), pos=nb.pos.numpy(), tr_sigma=nb.tr_sigma.numpy(),
+            rot_sigma=nb.rot_sigma.numpy(), rot_score=nb.rot_score.numpy(), tr_score=nb.tr_score.numpy(),
+            ads_center_noise_vec=nb.ads_center_noise_vec.numpy(), out1=out1.detach().numpy(),
+            out2=out2.detach().numpy(), loss=loss.detach().numpy(), g_out1=out1.grad.numpy(), g_out2=out2.grad.numpy())
+        print(f"train_{case}: loss {float(loss):.6f}")
+
+
 if __name__ == "__main__":
     import argparse
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--sampler-only", nargs="*", default=None,
                     help="regenerate only the named sampler fixtures (e.g. sampler100 sampler_sde)")
+    ap.add_argument("--training-only", action="store_true", help="regenerate only igso3.npz / train_*.npz")
     a = ap.parse_args()
-    if a.sampler_only is not None:
+    if a.training_only:
+        training_goldens(ref_import.load())
+    elif a.sampler_only is not None:
         ns_ = ref_import.load()
         m_ = ns_.PaiNN(None, 0, 1, scale_file=ns_.scale_file, so3_denoising=True).eval()
         sampler_goldens(ns_, m_, only=a.sampler_only or None)

@@ -59,9 +59,9 @@ def test_no_cpu_fallback(weights):
         m(b)  # CPU tensors: must fail loudly, not fall back
 
 
-def test_training_forward_is_refused():
+def test_training_forward_has_no_cpu_fallback_either():
     m = PaiNN(None, 0, 1, so3_denoising=True).train()
-    with torch.enable_grad(), pytest.raises(NotImplementedError):
+    with torch.enable_grad(), pytest.raises(_cabi.AdkError):
         m(S.make_batch(1))
 
 
