@@ -18,7 +18,7 @@
 //   warps 4-11 epilogue    : the tensor core's fp32 accumulate truncates (measured: error grows
 //                            linearly with the number of accumulate steps, 5e-7 at K=64 -> 4.8e-6 at
 //                            K=1024 of the output scale), so the TMEM accumulator only ever holds a
-//                            PARTIAL sum over TC_PROMOTE k-blocks (K=64, 12 MMA steps); these warps
+//                            PARTIAL sum over TC_PROMOTE = 2 k-blocks (K=128, 24 MMA steps); these warps
 //                            drain it (tcgen05.ld 32 lanes x 32 columns at a time) into fp32 register
 //                            sums with round-to-nearest adds while the MMA warp fills the other TMEM
 //                            slot, then apply scale + bias + activation and write fp32 and/or the
@@ -27,15 +27,21 @@
 //                            shared-memory buffer before the store: every 32-byte sector is written
 //                            once and whole (the row-per-lane store cost 1.9x DRAM write
 //                            amplification and 35 % of the tile time at K = 512).
-// Truncation-bias compensation: with the corrections issued first, the four hi*hi steps of a
-// k-block still shrink the partial sum's magnitude by a data-independent mean of 8.9e-8 relative
-// (measured on random-sign operands for K = 64..1024; 1.9e-7 on all-positive ones; an fp32 SGEMM
-// measures < 1e-9).  Unlike rounding noise this bias is coherent: it compounds linearly through
-// the ~36 chained GEMMs of a PaiNN forward (3e-6).  The drain therefore scales 3 of every 4
-// partial sums by (1 + 2^-23), i.e. by 1 + 8.9e-8 on average, which centres the error.
+// Truncation-bias compensation: with the corrections issued first, the hi*hi steps of a partial sum
+// still shrink its magnitude by a data-independent mean -- 8.9e-8 relative for the four steps of one
+// k-block (measured on random-sign operands for K = 64..1024; 1.9e-7 on all-positive ones; an fp32
+// SGEMM measures < 1e-9).  Unlike rounding noise this bias is coherent: it compounds linearly through
+// the ~36 chained GEMMs of a PaiNN forward.  The drain therefore scales every partial sum by a fixed
+// gain.  Round 2 promotes every TWO k-blocks (TC_PROMOTE = 2: half the TMEM hand-offs, +18 % GEMM
+// throughput); the bias of an eight-step partial is not twice the four-step one but 2.0 * 2^-23
+// (scripts/tc_gain_sweep.sh: end-to-end error of both heads against fp64 on four cases for gains of
+// 0 .. 3 units of 2^-23 per partial -- 2e-5 uncompensated, minimum 2.3-4.2e-6 at 2.0, i.e. (1 + 2^-22);
+// one k-block per promotion with its 0.75-unit gain measured 1.0-3.2e-6).  ADK_TC_GAIN="n0,n1"
+// overrides the gain of even / odd partials (units of 2^-23) for that calibration script.
 // Reference arithmetic replaced: the torch.nn.Linear calls of PaiNNMessage.x_proj, PaiNNUpdate.vec_proj /
 // xvec_proj and GatedEquivariantBlock (models/painn/painn_denoising.py:508-512, 580-587, 667-676).
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
 #include <cuda_fp16.h>
 
@@ -50,11 +56,12 @@ using namespace adk::tc;
 // single-CTA kernel at one k-block per promotion (the TMEM hand-off to the drain warps, now with remote arrivals, is the
 // critical path; both reach the same 1.13 PFLOP/s when two k-blocks are promoted at once), so it is off by default.
 bool g_tc_pair = false;
+float g_tc_gain[2] = {1.0000002384185791015625f, 1.0000002384185791015625f};  // even / odd two-k-block partial sums (ADK_TC_GAIN)
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_UMMA_K = 16;
 constexpr int TC_THREADS = 384;      // warpgroup 0: TMA warp, MMA warp, two idle; warpgroups 1-2: 8 epilogue warps
 constexpr int TC_EPI_WARP0 = 4;      // first epilogue warp
-constexpr int TC_PROMOTE = 1;        // k-blocks accumulated in TMEM before promotion to registers
+constexpr int TC_PROMOTE = 2;        // k-blocks accumulated in TMEM before promotion to registers
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;                      // 16 KB
 constexpr int TC_MAX_N = 2048;                                          // bias staged in shared memory
 constexpr uint32_t TC_XPOSE_BYTES = 32 * 64;                            // per epilogue warp: 32 rows x 16 fp32, swizzled
@@ -79,6 +86,7 @@ struct TcParams {
     int w_lo_row;   // same for W (= N)
     const float* bias;
     float acc_scale;
+    float gain0, gain1;
     int act;
     float* out_f32;
     int64_t ldc;
@@ -265,7 +273,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)astage * TC_BN +
                                        (uint32_t)half * TC_EPI_COLS;
                 // RZ compensation (see header comment): 3 partial sums out of 4 are scaled by 1 + 2^-23
-                const float gain = ((ch & 3) != 3) ? 1.00000011920928955078125f : 1.0f;
+                const float gain = (num_k - ch * TC_PROMOTE >= 2) ? ((ch & 1) ? P.gain1 : P.gain0) : 1.00000011920928955078125f;
                 if (TC_EPI_COLS >= 64) {
                     // two loads in flight per wait: the ~230-cycle round trip of a tcgen05.ld is paid twice per
                     // drain instead of four times (the drain is the pace-setter of this kernel)
@@ -460,6 +468,7 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     P.M = M; P.N = N; P.K = K;
     P.a_lo_row = (int)a_plane_rows; P.w_lo_row = N;
     P.bias = bias; P.acc_scale = acc_scale; P.act = act;
+    P.gain0 = g_tc_gain[0]; P.gain1 = g_tc_gain[1];
     P.out_f32 = out_f32; P.ldc = ldc;
     P.out_split = reinterpret_cast<__half*>(out_split);
     P.out_split_plane = out_plane_rows * (int64_t)N;
@@ -544,5 +553,12 @@ int adk_linear_tc_set_attrs() {
 #undef ADK_TC_ATTR
 #undef ADK_TC_ATTR1
     if (const char* e = getenv("ADK_TC_PAIR")) g_tc_pair = e[0] != '0';
+    if (const char* e = getenv("ADK_TC_GAIN")) {   // calibration knob: "n0,n1" in units of 2^-23
+        int n0 = 2, n1 = 2;
+        if (sscanf(e, "%d,%d", &n0, &n1) == 2) {
+            g_tc_gain[0] = 1.0f + (float)n0 * 1.1920928955078125e-07f;
+            g_tc_gain[1] = 1.0f + (float)n1 * 1.1920928955078125e-07f;
+        }
+    }
     return (int)e2;
 }

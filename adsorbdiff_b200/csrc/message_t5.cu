@@ -68,8 +68,10 @@ constexpr float T5_RBF_SCALE = 1024.0f;
 #ifdef T5_TRACE
 __device__ long long g_t5_trace[T5_MAX_TILES * 16];
 #define T5_STAMP(ti, ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && phase == 0 && lane == 0) g_t5_trace[(ti) * 16 + (ev)] = clock64(); } while (0)
+#define T5_CTA_STAMP(ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_t5_trace[(T5_MAX_TILES - 1) * 16 + (ev)] = clock64(); } while (0)
 #else
 #define T5_STAMP(ti, ev) do { } while (0)
+#define T5_CTA_STAMP(ev) do { } while (0)
 #endif
 
 struct T5Params {
@@ -287,6 +289,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
     const int a0 = P.atom_off[b], n = P.atom_off[b + 1] - a0;
     const int F = P.F, R = P.R;
     const bool has_vec = P.vec_in != nullptr;
+    T5_CTA_STAMP(0);
 
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (warp == 0) {
@@ -373,6 +376,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
     const int ntiles = *s_ntiles;
     const int nsel = s_ntiles[1];
     const int nphases = has_vec ? 2 : 1;
+    T5_CTA_STAMP(1);
 
     // Every role runs the same phase skeleton -- stage the sources, __syncthreads, its loop over the tiles,
     // __syncthreads -- inside its own branch, which opens with its own setmaxnreg (so ptxas applies that budget there).
@@ -395,6 +399,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
             }
             stage_sources(P, s_src, phase, a0, n, f0);
             __syncthreads();
+            T5_CTA_STAMP(2 + 3 * phase);
             if (warp == 0 && lane == 0) {
                 const uint32_t tile0 = (uint32_t)phase * (uint32_t)ntiles;
                 const uint32_t idesc = (1u << 4) | ((uint32_t)(T5_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -454,7 +459,9 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                     T5_STAMP(ti, 7);
                 }
             }
+            T5_CTA_STAMP(3 + 3 * phase);
             __syncthreads();   // everybody is done with this phase's weights, sources and partial vec_out
+            T5_CTA_STAMP(4 + 3 * phase);
         }
     } else if (warp < T5_EPI_WARP0) {
         // ===================== generator warpgroups, one column each =====================
@@ -721,6 +728,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    T5_CTA_STAMP(8);
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
