@@ -55,7 +55,9 @@ SIGNATURES = {
     "adk_message_t5": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_int, c_int,
                                c_float, c_int, c_float, _P, _P, _P, c_int64, c_float, _P, _P]),
     "adk_message_bwd_scratch_floats": (c_int64, [c_int, c_int, c_int, _P]),
-    "adk_message_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int,
+    "adk_message_bwd_plan_ints": (c_int64, [c_int, c_int64]),
+    "adk_message_bwd_plan": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, c_int, _P, _P]),
+    "adk_message_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int,
                                 _P, _P, _P, _P, _P, _P, _P, _P]),
     "adk_update_prep": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int64, c_float, _P, _P]),
     "adk_update_gate": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P, c_int64, c_float, _P, _P]),
@@ -81,7 +83,7 @@ launch_count = 0  # kernels launched through this binding (bench.py reports it)
 
 _LAUNCHES = {  # kernels behind one entry-point call
     "adk_neighbors": 1, "adk_export_edges": 2, "adk_embed": 1, "adk_layernorm": 1, "adk_linear": 1, "adk_split_f16": 1, "adk_split_f16_multi": 1, "adk_linear_tc": 1,
-    "adk_message": 1, "adk_message_mma": 1, "adk_message_t5": 1, "adk_message_bwd": 4, "adk_split_f16_transpose": 1, "adk_update_prep": 1, "adk_update_gate": 1, "adk_head_prep": 1, "adk_head_gate": 1, "adk_gather_rows": 1, "adk_scatter_rows": 1, "adk_mark_sources": 2,
+    "adk_message": 1, "adk_message_mma": 1, "adk_message_t5": 1, "adk_message_bwd": 4, "adk_message_bwd_plan": 1, "adk_split_f16_transpose": 1, "adk_update_prep": 1, "adk_update_gate": 1, "adk_head_prep": 1, "adk_head_gate": 1, "adk_gather_rows": 1, "adk_scatter_rows": 1, "adk_mark_sources": 2,
     "adk_init_placement": 1, "adk_se3_step": 2, "adk_early_stop": 2,
 }
 

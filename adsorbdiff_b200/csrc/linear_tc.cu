@@ -52,10 +52,12 @@ namespace {
 
 using namespace adk::tc;
 
-// Wide GEMMs as cta_group::2 pairs (adk_set_tc_pair / ADK_TC_PAIR=1).  Parity-green, but measured 13 % slower than the
-// single-CTA kernel at one k-block per promotion (the TMEM hand-off to the drain warps, now with remote arrivals, is the
-// critical path; both reach the same 1.13 PFLOP/s when two k-blocks are promoted at once), so it is off by default.
-bool g_tc_pair = false;
+// Wide GEMMs run as cta_group::2 pairs (two SMs share one 256 x 256 tile: each loads its own A rows and half of the
+// weight tile, so the operand bytes per SM and MMA drop by a third).  Bit-identical to the single-CTA kernel
+// (tests/test_gpu_linear_tc.py).  At one k-block per promotion the remote TMEM hand-off made it 13 % slower; at two it is
+// 5 % faster (417 against 397 useful TFLOP/s on the 1024 x 512 GEMMs), so it is on by default; adk_set_tc_pair(0) /
+// ADK_TC_PAIR=0 selects the single-CTA kernel.
+bool g_tc_pair = true;
 float g_tc_gain[2] = {1.0000002384185791015625f, 1.0000002384185791015625f};  // even / odd two-k-block partial sums (ADK_TC_GAIN)
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_UMMA_K = 16;

@@ -15,195 +15,228 @@
 //    pass over row j of the SAME in-edge CSR does it: the BWD instantiation of the forward kernel (csrc/message.cu),
 //    which gathers (g_x, g_v) of the atom at the other end where the forward gathers (xh, vec).
 //  * d_W[r][k] = sum_e d_r[e][r] * rbf_k(e) is a [3F x E] . [E x R] contraction over all edges with a banded right
-//    operand (16 live taps per edge).  `message_bwd_weights_kernel`: a half-warp owns 4 features; its 16 lanes are the
-//    16 residues k mod 16, so for every edge each lane has exactly one live tap (one exp per lane, no redundancy) and
-//    keeps the 8 taps of its residue x 3 projections x 4 features in registers.  Lanes 0-11 each compute one of the 12
-//    per-edge factors d_r and the half-warp exchanges them by shuffle.  A CTA walks a chunk of target rows; the chunks'
-//    partial sums are added in a fixed order by `reduce_chunks_kernel`.
+//    operand (16 live taps per edge), as many FLOPs as rbf_proj itself.  A thread owns one feature (its three
+//    projection rows): every gather is a coalesced 128-byte line per warp and the per-edge factors d_r need no
+//    exchange between lanes.  The difficulty is the accumulator: 3 x 128 sums per thread do not fit registers, and
+//    the 16-tap window moves with the edge's distance.  Solution: `message_bwd_plan_kernel` (once per graph, reused by
+//    the six layers) sorts each row chunk's edges by q = klo >> 4 into a flat list (stable, deterministic) that
+//    carries everything per edge (source, target row, scaled distance, envelope, unit vector).  The weight kernel
+//    walks that list: during pass q only the 32 taps [16 q, 16 q + 32) can be live, they sit in 96 registers, the
+//    lower half is STORED (each partial-sum slot is written exactly once, no read-modify-write, no shared-memory
+//    accumulators) when the pass ends and the upper half becomes the lower half of the next pass.  The 32 tap values
+//    of an edge are evaluated by the 32 lanes of the warp (one exp each) and broadcast through 128 bytes of shared
+//    memory.  Chunks' partial sums are added in a fixed order by `reduce_chunks_kernel`.
 // Exact fp32 SIMT arithmetic: this is the training path (tens of systems per GPU per step).
 #include "common.cuh"
 
 namespace {
 
 constexpr int BW_TAPS = 16;
+constexpr int BW_SLOTS = 8;          // R = 128 = 8 slots of 16 taps
+constexpr int BW_HDR = 16;           // ints per chunk header: [0..8] list offsets of the 8 passes (+ end), [9] i0, [10] i1
+constexpr int BW_ENTRY = 12;         // ints per list entry: {src, row, klo, -} {s, env, -, -} {rx, ry, rz, -}
+constexpr int BWP_THREADS = 128;
+constexpr int BWP_MAX_ROWS = 2048;   // rows per chunk the plan kernel can rank (dynamic shared memory: 9 ints per row)
+constexpr int BWW_THREADS = 128;     // = features per CTA of the weight kernel
 
 struct BwParams {
-    const int32_t* row_start;
-    const int32_t* row_deg;
-    const int32_t* e_src;
-    const float4* e_geo;
     const float* xh;        // [N][3F]
     const float* vec;       // [N][3][F] or null (layer 0)
-    const float* w;         // [3F][R]
-    const float* b;         // [3F]
     const float* offset;    // [R] Gaussian centres (scaled distance)
     const float* g_x;       // [N][F]
     const float* g_v;       // [N][3][F]
-    int N, F, R;
-    float inv_cutoff, coeff, env_a, env_b, env_c;
-    int env_p;
-    float k2, k3;
+    const int32_t* plan;
+    int N, F, R, chunks;
+    float coeff, k2, k3;
 };
 
-constexpr int BWW_THREADS = 256;
-constexpr int BWW_F = 64;        // features per CTA: 8 warps x 2 half-warps x 4 features
-constexpr int BWW_SLOTS = 8;     // taps per residue lane (R = 128 = 16 residues x 8)
-
-struct EdgeData {
-    float a, u0, u1, u2;
-};
-constexpr int BWW_EB = 4;        // edges whose gathers are issued together (two such sets are in flight)
-constexpr int BWW_STAGE = 128;   // edge records staged per pass (rows longer than this take several passes)
-
-// grid (F / 64, chunks), 256 threads, 2 CTAs per SM.
-// dynamic smem: the accumulators [8 slots x 12][256 threads] (a thread's own column: conflict-free, dynamic slot index)
-__global__ void __launch_bounds__(BWW_THREADS, 2) message_bwd_weights_kernel(BwParams P, int rows_per_chunk,
-                                                                            float* __restrict__ part_w,
-                                                                            float* __restrict__ part_b) {
-    extern __shared__ __align__(16) float s_acc[];
-    __shared__ int4 s_rec[BWW_STAGE];                 // {src, klo, s, env}
-    __shared__ float4 s_rh[BWW_STAGE];                // unit vector
-    __shared__ float s_mu[16 * BWW_SLOTS];
-    __shared__ __align__(16) float s_dr[BWW_THREADS / 32][BWW_EB][2][16];
-    const int F = P.F, R = P.R, tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int m = lane & 15, half = lane >> 4;
-    const int fq = blockIdx.x * BWW_F + (warp * 2 + half) * 4;      // first of this half-warp's 4 features
-    const int v = m < 12 ? m : 0;                                   // the per-edge factor this lane computes
-    const int vg = v >> 2, vf = fq + (v & 3);
-    const bool has_vec = P.vec != nullptr;
-    const float kg = vg == 1 ? P.k2 : P.k3;
-    for (int k = tid; k < BWW_SLOTS * 12 * BWW_THREADS; k += BWW_THREADS) s_acc[k] = 0.f;
-    for (int k = tid; k < R; k += BWW_THREADS) s_mu[k] = P.offset[k];
-    // Within a row the edges are sorted by distance, so q0 = klo >> 4 only grows: lane m's live tap sits in slot q0
-    // (m >= klo & 15) or q0 + 1 (m < klo & 15).  Two register sets follow the row; they are folded into the shared
-    // accumulators when q0 moves (a warp-uniform event, a handful of times per row).
-    float lo[12], hi[12];
+// One CTA per chunk of target rows.  klo = first of the 16 live centres, exactly as the forward kernels pick it.
+__global__ void __launch_bounds__(BWP_THREADS) message_bwd_plan_kernel(
+    const int32_t* __restrict__ row_start, const int32_t* __restrict__ row_deg, const int32_t* __restrict__ e_src,
+    const float4* __restrict__ e_geo, int N, int R, int rows_per_chunk, float inv_cutoff, int env_p, float env_a,
+    float env_b, float env_c, int32_t* __restrict__ plan, int chunks) {
+    extern __shared__ int s_cnt[];   // [rows][9]: per row the number of edges per pass, then their list offsets
+    __shared__ int s_red[BWP_THREADS];
+    __shared__ int s_tot[BW_SLOTS + 1];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const int i0 = min(N, c * rows_per_chunk), i1 = min(N, i0 + rows_per_chunk), nrows = i1 - i0;
+    auto klo_of = [&](float d) {
+        const float sc = d * inv_cutoff;
+        int klo = (int)floorf(sc * (float)(R - 1)) - 7;
+        return max(0, min(klo, R - BW_TAPS));
+    };
+    // edges before this chunk (the list is packed in row order)
+    int before = 0;
+    for (int i = tid; i < i0; i += BWP_THREADS) before += row_deg[i];
+    s_red[tid] = before;
+    for (int r = tid; r < nrows; r += BWP_THREADS) {
+        int cnt[BW_SLOTS];
 #pragma unroll
-    for (int u = 0; u < 12; ++u) lo[u] = hi[u] = 0.f;
-    int q0cur = 0;
-    float db = 0.f;
-    auto fold = [&](const float (&r)[12], int q) {
-        if (q < BWW_SLOTS) {
+        for (int q = 0; q < BW_SLOTS; ++q) cnt[q] = 0;
+        const int start = row_start[i0 + r], deg = row_deg[i0 + r];
+        for (int e = 0; e < deg; ++e) {
+            const int q = klo_of(e_geo[start + e].x) >> 4;
 #pragma unroll
-            for (int u = 0; u < 12; ++u) s_acc[(q * 12 + u) * BWW_THREADS + tid] += r[u];
+            for (int u = 0; u < BW_SLOTS; ++u) cnt[u] += (u == q) ? 1 : 0;
         }
+#pragma unroll
+        for (int q = 0; q < BW_SLOTS; ++q) s_cnt[r * 9 + q] = cnt[q];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int b = 0;
+        for (int t = 0; t < BWP_THREADS; ++t) b += s_red[t];
+        s_tot[BW_SLOTS] = b;   // base of this chunk's list region
+    }
+    if (tid < BW_SLOTS) {      // pass tid: exclusive scan of its per-row counts
+        int run = 0;
+        for (int r = 0; r < nrows; ++r) {
+            const int v = s_cnt[r * 9 + tid];
+            s_cnt[r * 9 + tid] = run;
+            run += v;
+        }
+        s_tot[tid] = run;
+    }
+    __syncthreads();
+    int pass_base[BW_SLOTS + 1];
+    pass_base[0] = s_tot[BW_SLOTS];
+#pragma unroll
+    for (int q = 0; q < BW_SLOTS; ++q) pass_base[q + 1] = pass_base[q] + s_tot[q];
+    if (tid <= BW_SLOTS) plan[c * BW_HDR + tid] = pass_base[tid];
+    if (tid == 9) plan[c * BW_HDR + 9] = i0;
+    if (tid == 10) plan[c * BW_HDR + 10] = i1;
+    int4* list = reinterpret_cast<int4*>(plan + (size_t)chunks * BW_HDR);
+    for (int r = tid; r < nrows; r += BWP_THREADS) {
+        int pos[BW_SLOTS];
+#pragma unroll
+        for (int q = 0; q < BW_SLOTS; ++q) pos[q] = pass_base[q] + s_cnt[r * 9 + q];
+        const int start = row_start[i0 + r], deg = row_deg[i0 + r];
+        for (int e = 0; e < deg; ++e) {
+            const float4 geo = e_geo[start + e];
+            const float sc = geo.x * inv_cutoff;
+            float sp = sc;
+            for (int u = 1; u < env_p; ++u) sp *= sc;
+            float env = 1.0f + env_a * sp;
+            sp *= sc; env += env_b * sp;
+            sp *= sc; env += env_c * sp;
+            env = sc < 1.0f ? env : 0.0f;
+            const int klo = klo_of(geo.x), q = klo >> 4;
+            int at = 0;
+#pragma unroll
+            for (int u = 0; u < BW_SLOTS; ++u)
+                if (u == q) at = pos[u]++;
+            int4* ent = list + (size_t)at * 3;
+            ent[0] = make_int4(e_src[start + e], i0 + r, klo, 0);
+            ent[1] = make_int4(__float_as_int(sc), __float_as_int(env), 0, 0);
+            ent[2] = make_int4(__float_as_int(geo.y), __float_as_int(geo.z), __float_as_int(geo.w), 0);
+        }
+    }
+}
+
+struct BwItem {
+    int4 a, b, c;          // the list entry
+};
+struct BwFeat {
+    float x[3], v[3], gx, gv[3];
+};
+
+// grid (F / 128, chunks), 128 threads (thread = feature), 3 CTAs per SM
+__global__ void __launch_bounds__(BWW_THREADS, 3) message_bwd_weights_kernel(BwParams P, float* __restrict__ part_w,
+                                                                            float* __restrict__ part_b) {
+    __shared__ __align__(16) float s_tap[BWW_THREADS / 32][2][32];
+    const int F = P.F, R = P.R;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x * BWW_THREADS + threadIdx.x;
+    const int c = blockIdx.y;
+    const bool has_vec = P.vec != nullptr;
+    const int32_t* hdr = P.plan + (size_t)c * BW_HDR;
+    const int4* list = reinterpret_cast<const int4*>(P.plan + (size_t)P.chunks * BW_HDR);
+    float W[3][32];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int r = 0; r < 32; ++r) W[g][r] = 0.f;
+    float db[3] = {0.f, 0.f, 0.f};
+    float* pw = part_w + (size_t)c * 3 * F * R;
+
+    auto load_item = [&](int idx) {
+        BwItem it;
+        const int4* e = list + (size_t)idx * 3;
+        it.a = e[0]; it.b = e[1]; it.c = e[2];
+        return it;
+    };
+    auto load_feat = [&](const BwItem& it) {
+        BwFeat ft;
+        const float* xs = P.xh + (size_t)it.a.x * 3 * F + f;
+        ft.x[0] = xs[0]; ft.x[1] = xs[F]; ft.x[2] = xs[2 * F];
+        ft.v[0] = ft.v[1] = ft.v[2] = 0.f;
+        if (has_vec) {
+            const float* vs = P.vec + (size_t)it.a.x * 3 * F + f;
+            ft.v[0] = vs[0]; ft.v[1] = vs[F]; ft.v[2] = vs[2 * F];
+        }
+        ft.gx = P.g_x[(size_t)it.a.y * F + f];
+        const float* gs = P.g_v + (size_t)it.a.y * 3 * F + f;
+        ft.gv[0] = gs[0]; ft.gv[1] = gs[F]; ft.gv[2] = gs[2 * F];
+        return ft;
     };
 
-    const int i0 = blockIdx.y * rows_per_chunk, i1 = min(P.N, i0 + rows_per_chunk);
-    for (int i = i0; i < i1; ++i) {
-        const int start = P.row_start[i], deg = P.row_deg[i];
-        if (deg == 0) continue;
-        const float gx = P.g_x[(size_t)i * F + vf];
-        const float g0 = P.g_v[((size_t)i * 3 + 0) * F + vf], g1 = P.g_v[((size_t)i * 3 + 1) * F + vf],
-                    g2 = P.g_v[((size_t)i * 3 + 2) * F + vf];
-        for (int p0 = 0; p0 < deg; p0 += BWW_STAGE) {
-            const int cnt = min(BWW_STAGE, deg - p0);
-            __syncthreads();   // everyone is done with the previous pass's records
-            if (tid < cnt) {   // per-edge record, computed once for the whole CTA
-                const float4 geo = P.e_geo[start + p0 + tid];
-                const float sc = geo.x * P.inv_cutoff;
-                float sp = sc;
-                for (int q = 1; q < P.env_p; ++q) sp *= sc;
-                float env = 1.0f + P.env_a * sp;
-                sp *= sc; env += P.env_b * sp;
-                sp *= sc; env += P.env_c * sp;
-                env = sc < 1.0f ? env : 0.0f;
-                int klo = (int)floorf(sc * (float)(R - 1)) - 7;
-                klo = max(0, min(klo, R - BW_TAPS));
-                s_rec[tid] = make_int4(P.e_src[start + p0 + tid], klo, __float_as_int(sc), __float_as_int(env));
-                s_rh[tid] = make_float4(geo.y, geo.z, geo.w, 0.f);
+    const int end_all = hdr[BW_SLOTS];
+    int idx = hdr[0];
+    int par = 0;
+    // software pipeline: entries two items ahead, gathers one item ahead
+    BwItem it0 = load_item(min(idx, max(end_all - 1, 0))), it1 = load_item(min(idx + 1, max(end_all - 1, 0)));
+    BwFeat f0 = load_feat(it0);
+    for (int q = 0; q < BW_SLOTS; ++q) {
+        const int end = hdr[q + 1];
+        for (; idx < end; ++idx) {
+            const BwItem it2 = load_item(min(idx + 2, end_all - 1));
+            const BwFeat f1 = load_feat(it1);
+            // this lane's tap of the pass window: centre 16 q + lane, live inside [klo, klo + 16)
+            const int o = it0.a.z - 16 * q;
+            const float sc = __int_as_float(it0.b.x), env = __int_as_float(it0.b.y);
+            const float diff = sc - P.offset[min(16 * q + lane, R - 1)];
+            const float tap = (lane >= o && lane < o + BW_TAPS) ? env * expf(P.coeff * diff * diff) : 0.f;
+            s_tap[warp][par][lane] = tap;
+            // the three per-edge factors of this feature
+            const float rx = __int_as_float(it0.c.x), ry = __int_as_float(it0.c.y), rz = __int_as_float(it0.c.z);
+            float dr[3];
+            dr[0] = f0.x[0] * f0.gx;
+            dr[1] = f0.x[1] * (f0.v[0] * f0.gv[0] + f0.v[1] * f0.gv[1] + f0.v[2] * f0.gv[2]) * P.k2;
+            dr[2] = f0.x[2] * (rx * f0.gv[0] + ry * f0.gv[1] + rz * f0.gv[2]) * P.k3;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) db[g] += dr[g];
+            __syncwarp();
+            const float4* tp = reinterpret_cast<const float4*>(s_tap[warp][par]);
+#pragma unroll
+            for (int r4 = 0; r4 < 8; ++r4) {
+                const float4 t4 = tp[r4];
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    W[g][4 * r4 + 0] = fmaf(dr[g], t4.x, W[g][4 * r4 + 0]);
+                    W[g][4 * r4 + 1] = fmaf(dr[g], t4.y, W[g][4 * r4 + 1]);
+                    W[g][4 * r4 + 2] = fmaf(dr[g], t4.z, W[g][4 * r4 + 2]);
+                    W[g][4 * r4 + 3] = fmaf(dr[g], t4.w, W[g][4 * r4 + 3]);
+                }
             }
-            __syncthreads();
-            auto load4 = [&](EdgeData (&d)[BWW_EB], int b) {
+            par ^= 1;   // the other buffer is free again after the __syncwarp of the NEXT item
+            it0 = it1; it1 = it2; f0 = f1;
+        }
+        // the pass is over: its lower 16 taps are final for this chunk
 #pragma unroll
-                for (int t = 0; t < BWW_EB; ++t) {
-                    const int e = b * BWW_EB + t;
-                    d[t].a = d[t].u0 = d[t].u1 = d[t].u2 = 0.f;
-                    if (e < cnt) {
-                        const int src = s_rec[e].x;
-                        d[t].a = P.xh[(size_t)src * 3 * F + vg * F + vf];
-                        if (vg == 1) {
-                            if (has_vec) {
-                                const float* vj = P.vec + (size_t)src * 3 * F + vf;
-                                d[t].u0 = vj[0]; d[t].u1 = vj[F]; d[t].u2 = vj[2 * F];
-                            }
-                        } else if (vg == 2) {
-                            const float4 rh = s_rh[e];
-                            d[t].u0 = rh.x; d[t].u1 = rh.y; d[t].u2 = rh.z;
-                        }
-                    }
-                }
-            };
-            auto compute4 = [&](const EdgeData (&d)[BWW_EB], int b) {
-                // phase 1 (branch-free, the four edges' chains interleave): this lane's factor and live tap per edge
-                float tap[BWW_EB];
-                int klo[BWW_EB];
-                __syncwarp();
+        for (int g = 0; g < 3; ++g) {
+            float4* dst = reinterpret_cast<float4*>(pw + (size_t)(g * F + f) * R + 16 * q);
 #pragma unroll
-                for (int t = 0; t < BWW_EB; ++t) {
-                    const int e = min(b * BWW_EB + t, cnt - 1);
-                    const float sdot = vg == 0 ? gx : (d[t].u0 * g0 + d[t].u1 * g1 + d[t].u2 * g2) * kg;
-                    const float dr = d[t].a * sdot;      // zero for edges past the end (d is zeroed)
-                    db += m < 12 ? dr : 0.f;
-                    s_dr[warp][t][half][m] = dr;
-                    const int4 r = s_rec[e];
-                    klo[t] = r.y;
-                    const int k = r.y + ((m - r.y) & 15);  // the tap with k = m (mod 16) inside [klo, klo + 16)
-                    const float diff = __int_as_float(r.z) - s_mu[k];
-                    tap[t] = __int_as_float(r.w) * expf(P.coeff * diff * diff);
-                }
-                __syncwarp();
-                // phase 2: 12 factors x this lane's tap, into the register set of its slot
+            for (int r4 = 0; r4 < 4; ++r4)
+                dst[r4] = make_float4(W[g][4 * r4], W[g][4 * r4 + 1], W[g][4 * r4 + 2], W[g][4 * r4 + 3]);
 #pragma unroll
-                for (int t = 0; t < BWW_EB; ++t) {
-                    if (b * BWW_EB + t >= cnt) break;
-                    const int q0 = klo[t] >> 4;
-                    if (q0 != q0cur) {
-                        fold(lo, q0cur);
-                        if (q0 == q0cur + 1) {
-#pragma unroll
-                            for (int u = 0; u < 12; ++u) lo[u] = hi[u];
-                        } else {
-                            fold(hi, q0cur + 1);
-#pragma unroll
-                            for (int u = 0; u < 12; ++u) lo[u] = 0.f;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 12; ++u) hi[u] = 0.f;
-                        q0cur = q0;
-                    }
-                    const float4* dv = reinterpret_cast<const float4*>(&s_dr[warp][t][half][0]);
-                    const float4 v0 = dv[0], v1 = dv[1], v2 = dv[2];
-                    const float val[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-                    const bool up = m < (klo[t] & 15);
-                    const float tl = up ? 0.f : tap[t], th = up ? tap[t] : 0.f;
-#pragma unroll
-                    for (int u = 0; u < 12; ++u) {
-                        lo[u] = fmaf(val[u], tl, lo[u]);
-                        hi[u] = fmaf(val[u], th, hi[u]);
-                    }
-                }
-            };
-            const int nb = (cnt + BWW_EB - 1) / BWW_EB;
-            EdgeData A[BWW_EB], B[BWW_EB];
-            load4(A, 0);
-            for (int b = 0; b < nb; b += 2) {
-                load4(B, b + 1);
-                compute4(A, b);
-                load4(A, b + 2);
-                if (b + 1 < nb) compute4(B, b + 1);
+            for (int r = 0; r < 16; ++r) {
+                W[g][r] = W[g][16 + r];
+                W[g][16 + r] = 0.f;
             }
         }
     }
-    fold(lo, q0cur);
-    fold(hi, q0cur + 1);
-    float* pw = part_w + (size_t)blockIdx.y * 3 * F * R;
-    for (int q = 0; q < BWW_SLOTS; ++q)
 #pragma unroll
-        for (int t = 0; t < 12; ++t)
-            pw[(size_t)((t >> 2) * F + fq + (t & 3)) * R + q * 16 + m] = s_acc[(q * 12 + t) * BWW_THREADS + tid];
-    if (m < 12) part_b[(size_t)blockIdx.y * 3 * F + vg * F + vf] = db;
+    for (int g = 0; g < 3; ++g) part_b[(size_t)c * 3 * F + g * F + f] = db[g];
 }
 
 // out[i] = sum over chunks (fixed order) of part[c][i]
@@ -217,47 +250,64 @@ __global__ void reduce_chunks_kernel(const float* __restrict__ part, int chunks,
 
 }  // namespace
 
+static int bwd_chunks(int N) {
+    int chunks = N < 111 ? N : 111;   // 4 x 111 CTAs of the weight kernel = one wave of 148 SMs x 3
+    const int need = (N + BWP_MAX_ROWS - 1) / BWP_MAX_ROWS;
+    return chunks < need ? need : chunks;
+}
+
 extern "C" int64_t adk_message_bwd_scratch_floats(int N, int F, int R, int* chunks_out) {
     if (N <= 0 || F <= 0 || R <= 0) return ADK_EINVAL;
-    int chunks = N < 37 ? N : 37;   // row chunks of the weight-gradient pass (8 x 37 CTAs = one wave of 148 SMs x 2)
+    const int chunks = bwd_chunks(N);
     if (chunks_out) *chunks_out = chunks;
     return (int64_t)chunks * 3 * F * (R + 1);
 }
 
+extern "C" int64_t adk_message_bwd_plan_ints(int N, int64_t e_cap) {
+    if (N <= 0 || e_cap < 0) return ADK_EINVAL;
+    return (int64_t)bwd_chunks(N) * BW_HDR + (int64_t)BW_ENTRY * e_cap;
+}
+
+extern "C" int adk_message_bwd_plan(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
+                                    const float* e_geo, int N, int R, float cutoff, int envelope_exponent,
+                                    int32_t* plan, void* stream) {
+    if (!row_start || !row_deg || !e_src || !e_geo || !plan || N <= 0) return ADK_EINVAL;
+    if (R != 16 * BW_SLOTS || envelope_exponent < 1) return ADK_EINVAL;
+    const int chunks = bwd_chunks(N);
+    const int rows_per_chunk = (N + chunks - 1) / chunks;
+    const double p = (double)envelope_exponent;
+    message_bwd_plan_kernel<<<chunks, BWP_THREADS, sizeof(int) * 9 * rows_per_chunk, adk::as_stream(stream)>>>(
+        row_start, row_deg, e_src, reinterpret_cast<const float4*>(e_geo), N, R, rows_per_chunk,
+        (float)(1.0 / (double)cutoff), envelope_exponent, (float)(-(p + 1) * (p + 2) / 2), (float)(p * (p + 2)),
+        (float)(-p * (p + 1) / 2), plan, chunks);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int adk_message_bwd(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const float* e_geo,
-                               const float* xh, const float* vec_in, const float* w_rbf, const float* b_rbf,
-                               const float* rbf_offset, int N, int F, int R, float cutoff, int envelope_exponent,
-                               const float* g_dx, const float* g_dvec, float* d_xh, float* d_vec, float* d_w,
-                               float* d_b, float* scratch, void* stream) {
-    if (!row_start || !row_deg || !e_src || !e_geo || !xh || !w_rbf || !b_rbf || !rbf_offset || !g_dx || !g_dvec ||
-        !d_xh || !d_vec || !d_w || !d_b || !scratch || N <= 0)
+                               const int32_t* plan, const float* xh, const float* vec_in, const float* w_rbf,
+                               const float* b_rbf, const float* rbf_offset, int N, int F, int R, float cutoff,
+                               int envelope_exponent, const float* g_dx, const float* g_dvec, float* d_xh, float* d_vec,
+                               float* d_w, float* d_b, float* scratch, void* stream) {
+    if (!row_start || !row_deg || !e_src || !e_geo || !plan || !xh || !w_rbf || !b_rbf || !rbf_offset || !g_dx ||
+        !g_dvec || !d_xh || !d_vec || !d_w || !d_b || !scratch || N <= 0)
         return ADK_EINVAL;
-    if (F % BWW_F != 0 || R != 16 * BWW_SLOTS || envelope_exponent < 1) return ADK_EINVAL;
+    if (F % BWW_THREADS != 0 || R != 16 * BW_SLOTS || envelope_exponent < 1) return ADK_EINVAL;
     int rc = adk_message_bwd_nodes(row_start, row_deg, e_src, e_geo, xh, vec_in, w_rbf, b_rbf, rbf_offset, N, F, R, cutoff,
                                    envelope_exponent, g_dx, g_dvec, d_xh, d_vec, stream);
     if (rc) return rc;
     BwParams P;
-    P.row_start = row_start; P.row_deg = row_deg; P.e_src = e_src; P.e_geo = reinterpret_cast<const float4*>(e_geo);
-    P.xh = xh; P.vec = vec_in; P.w = w_rbf; P.b = b_rbf; P.offset = rbf_offset; P.g_x = g_dx; P.g_v = g_dvec;
-    P.N = N; P.F = F; P.R = R;
-    P.inv_cutoff = (float)(1.0 / (double)cutoff);
+    P.xh = xh; P.vec = vec_in; P.offset = rbf_offset; P.g_x = g_dx; P.g_v = g_dvec; P.plan = plan;
+    P.N = N; P.F = F; P.R = R; P.chunks = bwd_chunks(N);
     const double spacing = 1.0 / (double)(R - 1);
     P.coeff = (float)(-0.5 / (spacing * spacing));
-    const double p = (double)envelope_exponent;
-    P.env_p = envelope_exponent;
-    P.env_a = (float)(-(p + 1) * (p + 2) / 2);
-    P.env_b = (float)(p * (p + 2));
-    P.env_c = (float)(-p * (p + 1) / 2);
     P.k2 = (float)(1.0 / sqrt(3.0 * (double)F));
     P.k3 = (float)(1.0 / sqrt((double)F));
     cudaStream_t st = adk::as_stream(stream);
-    int chunks = 0;
-    adk_message_bwd_scratch_floats(N, F, R, &chunks);
-    const int rows_per_chunk = (N + chunks - 1) / chunks;
+    const int chunks = P.chunks;
     float* part_w = scratch;
     float* part_b = scratch + (size_t)chunks * 3 * F * R;
-    const size_t smem = sizeof(float) * BWW_SLOTS * 12 * BWW_THREADS;
-    message_bwd_weights_kernel<<<dim3(F / BWW_F, chunks), BWW_THREADS, smem, st>>>(P, rows_per_chunk, part_w, part_b);
+    message_bwd_weights_kernel<<<dim3(F / BWW_THREADS, chunks), BWW_THREADS, 0, st>>>(P, part_w, part_b);
     ADK_LAUNCH_CHECK();
     const int64_t nw = (int64_t)3 * F * R, nb = (int64_t)3 * F;
     reduce_chunks_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(part_w, chunks, nw, d_w);
@@ -268,6 +318,6 @@ extern "C" int adk_message_bwd(const int32_t* row_start, const int32_t* row_deg,
 }
 
 int adk_message_bwd_set_attrs() {
-    return (int)cudaFuncSetAttribute(message_bwd_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(float) * BWW_SLOTS * 12 * BWW_THREADS));
+    return (int)cudaFuncSetAttribute(message_bwd_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(int) * 9 * BWP_MAX_ROWS));
 }

@@ -70,7 +70,7 @@ class MessageFn(torch.autograd.Function):
         d_b = torch.empty(3 * F_, **f32)
         n_scratch = _cabi.load().adk_message_bwd_scratch_floats(N, F_, R, None)
         scratch = torch.empty(n_scratch, **f32)
-        call("adk_message_bwd", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(xh),
+        call("adk_message_bwd", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(p.bwd_plan), ptr(xh),
              ptr(vec_in) if ctx.has_vec else None, ptr(w), ptr(b), ptr(net.radial_basis.rbf.offset), N, F_, R,
              float(net.cutoff), net.radial_basis.exponent, ptr(g_dx), ptr(g_dvec), ptr(d_xh), ptr(d_vec), ptr(d_w),
              ptr(d_b), ptr(scratch))
@@ -96,15 +96,47 @@ def _gated_block(blk, x, v, out_channels: int):
     return _ssilu(xo), g.unsqueeze(1) * vec2
 
 
+def _status_to_host(net, p) -> None:
+    """Copy the status word to pinned host memory on a side stream, right behind the kernels that set it (neighbour
+    search, element check): reading it later costs no drain of the main stream."""
+    io = getattr(net, "_status_io", None)
+    if io is None or io["device"] != p.device:
+        io = net._status_io = {"device": p.device, "host": torch.zeros(1, dtype=torch.int32).pin_memory(),
+                               "stream": torch.cuda.Stream(p.device), "event": torch.cuda.Event()}
+    io["stream"].wait_stream(torch.cuda.current_stream(p.device))
+    with torch.cuda.stream(io["stream"]):
+        io["host"].copy_(p.status, non_blocking=True)
+        io["event"].record(io["stream"])
+
+
+def check_status_async(net, p) -> None:
+    """Raise what `PaiNN.check_status` raises, from the side-stream copy made by the forward."""
+    io = net._status_io
+    io["event"].synchronize()
+    if int(io["host"][0]):
+        net.check_status(p)
+
+
 def forward_train(net, data, check: bool = True):
     """The differentiable forward of `adsorbdiff_b200.PaiNN` (PaiNN.forward, painn_denoising.py:402-481).  Returns
-    forces [N,3] (and forces2 with `so3_denoising`) attached to the autograd graph of the parameters.  `check` reads
-    the device status word (empty system, bad element, row overflow) before returning -- one host sync; `TrainStep`
-    defers it until the backward pass has been enqueued."""
+    forces [N,3] (and forces2 with `so3_denoising`) attached to the autograd graph of the parameters.  `check` raises
+    on the device status word (empty system, bad element, row overflow) before returning; it waits only for the
+    neighbour search, not for the forward.  `TrainStep` defers it until the backward pass has been enqueued."""
     p, z, pos = net._prepare(data)
     net._graph(p, pos)
+    if torch.is_grad_enabled():
+        # the weight-gradient pass walks the edges sorted by tap slot: planned once per graph, used by every layer
+        if getattr(p, "bwd_plan", None) is None:
+            n_int = _cabi.load().adk_message_bwd_plan_ints(p.N, p.e_src.numel())
+            p.bwd_plan = torch.empty(n_int, dtype=torch.int32, device=p.device)
+        call("adk_message_bwd_plan", p.device, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), p.N,
+             net.num_rbf, float(net.cutoff), net.radial_basis.exponent, ptr(p.bwd_plan))
     F_ = net.hidden_channels
-    x = net.atom_emb.embeddings(z - 1)
+    ne = net.atom_emb.embeddings.weight.shape[0]
+    bad = ((z < 1) | (z > ne)).any()    # the reference's embedding raises IndexError; torch's CUDA lookup would assert
+    p.status.bitwise_or_(bad.to(torch.int32) * _cabi.STATUS_BAD_ELEMENT)
+    _status_to_host(net, p)
+    x = net.atom_emb.embeddings(z.clamp(1, ne) - 1)
     vec = None
     for l in range(net.num_layers):
         m, u = net.message_layers[l], net.update_layers[l]
@@ -125,7 +157,7 @@ def forward_train(net, data, check: bool = True):
         outs.append(hv.squeeze(-1))
     net._train_plan = p
     if check:
-        net.check_status(p)
+        check_status_async(net, p)
     return outs[0] if not net.so3_denoising else tuple(outs)
 
 
@@ -354,7 +386,7 @@ class TrainStep:
         loss = denoising_loss(out, batch, self.tables)
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
-        net.check_status(net._train_plan)   # raises before the optimizer sees gradients of a malformed batch
+        check_status_async(net, net._train_plan)   # raises before the optimizer sees gradients of a malformed batch
         if self.world > 1:
             allreduce_mean_([q.grad for q in self.params if q.grad is not None])
         if self.clip:

@@ -632,7 +632,7 @@ def reference_train_rate(batch, steps, warmup, device):
         torch._foreach_lerp_(shadow, [q.detach() for q in params], 1e-3)
         float(loss)
     torch.cuda.synchronize()
-    return batch.num_graphs * steps / (time.perf_counter() - t0)
+    return batch.num_graphs * steps / (time.perf_counter() - t0), torch.cuda.max_memory_allocated(device) / 2**30
 
 
 def run_train(args):
@@ -699,8 +699,10 @@ def run_train(args):
     if rank == 0 and not args.quick:
         try:
             ref_b = min(B, args.train_ref_batch)
-            ref_rate = reference_train_rate(S.collate([S.make_system(i) for i in range(ref_b)]), 3, 2, str(dev))
-            ref = {"value": ref_rate, "unit": "systems/s", "batch": ref_b,
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats(dev)
+            ref_rate, ref_mem = reference_train_rate(S.collate([S.make_system(i) for i in range(ref_b)]), 3, 2, str(dev))
+            ref = {"value": ref_rate, "unit": "systems/s", "batch": ref_b, "peak_mem_gib": ref_mem,
                    "what": "reference PaiNN module (its torch ops, torch autograd) on this GPU, same step"}
         except Exception as e:
             ref = {"unavailable": f"{type(e).__name__}: {e}"[:200]}

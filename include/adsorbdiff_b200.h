@@ -134,7 +134,8 @@ int adk_linear(const float* A, int64_t lda, const float* W, const float* bias, i
 int adk_split_f16(const float* src, int64_t ld, int M, int K, float scale, void* dst, int64_t plane_rows,
                   uint32_t* status, void* stream);
 /* Tuning knob: run wide GEMMs as cta_group::2 CTA pairs (one MMA over M = 256 rows, each CTA staging half of the
- * weight tile).  Off by default (slower at one k-block per promotion, see csrc/linear_tc.cu); also ADK_TC_PAIR=1. */
+ * weight tile).  On by default (5 % faster at two k-blocks per promotion, bit-identical results; see csrc/linear_tc.cu);
+ * ADK_TC_PAIR=0 in the environment also turns it off. */
 int adk_set_tc_pair(int enable);
 
 /* Same split for `count` contiguous tensors in one launch: table[i] = {const float* src; fp16* dst;
@@ -212,10 +213,17 @@ int adk_message_t5(const int32_t* atom_off, int B, int n_max,
  * Uses the symmetry of the edge list (every edge has a mirror of equal length and negated unit vector), so the
  * transposed aggregation is a walk over the same in-edge CSR.  Exact fp32, deterministic.  F % 128 == 0.
  * scratch: adk_message_bwd_scratch_floats(N, F, R, NULL) floats.  vec_in may be NULL (first layer: vec == 0).
+ * plan: the edges of each row chunk sorted by the 16-centre slot their Gaussian window starts in, with everything
+ *   the weight-gradient pass needs per edge; built once per graph by adk_message_bwd_plan (R == 128) into
+ *   adk_message_bwd_plan_ints(N, e_cap) int32 (e_cap >= number of edges, e.g. the capacity of e_src) and reused by
+ *   every layer's backward.
  */
 int64_t adk_message_bwd_scratch_floats(int N, int F, int R, int* chunks_out /* may be NULL */);
+int64_t adk_message_bwd_plan_ints(int N, int64_t e_cap);
+int adk_message_bwd_plan(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const float* e_geo,
+                         int N, int R, float cutoff, int envelope_exponent, int32_t* plan, void* stream);
 int adk_message_bwd(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src, const float* e_geo,
-                    const float* xh, const float* vec_in, const float* w_rbf, const float* b_rbf,
+                    const int32_t* plan, const float* xh, const float* vec_in, const float* w_rbf, const float* b_rbf,
                     const float* rbf_offset, int N, int F, int R, float cutoff, int envelope_exponent,
                     const float* g_dx, const float* g_dvec, float* d_xh, float* d_vec, float* d_w, float* d_b,
                     float* scratch, void* stream);

@@ -1,10 +1,11 @@
 """Training step on the GPU: gradients of the differentiable forward against the fp64
 autograd of the oracle, the message backward kernel alone, and the optimisation step.
 
-Bars: the training forward equals the exact-fp32 inference forward to 1e-6 of the output's max magnitude (same
-arithmetic, torch ops instead of the fused node-wise kernels); every parameter gradient is within 1e-4 of the
-tensor's max |gradient| computed by fp64 autograd through `oracle.painn_oracle.painn_forward` (fp32 forward AND
-backward; the reference's own fp32 autograd sits at the same distance from fp64)."""
+Bars (relative to the tensor's max magnitude): outputs of the training forward within 1e-5 of the fp64 oracle; every
+parameter gradient within 3e-5 of fp64 autograd through `oracle.painn_oracle.painn_forward`, AND no further from it
+than twice the distance of the same oracle run in fp32 on the CPU (= the reference's arithmetic: torch ops + torch
+autograd in fp32), which is measured in the same test and printed: 1e-5 is the fp32 noise floor of this network's
+backward pass, not a property of the kernels (the message backward alone is at 1e-6, `test_message_backward_alone`)."""
 import numpy as np
 import pytest
 import torch
@@ -15,7 +16,7 @@ from tests.cases import CASES
 
 pytestmark = pytest.mark.gpu
 
-GRAD_TOL = 1e-4
+GRAD_TOL = 3e-5
 PARAMS = dict(num_steps=100, ads_std_low=0.1, ads_std_high=10, rot_std_low=0.01, rot_std_high=1.55,
               free_std_low=0.01, free_std_high=0.1)
 
@@ -27,27 +28,28 @@ def net(weights):
     return m
 
 
-def _oracle_grads(weights, b, G1, G2):
-    P = {k: (v.double().clone().requires_grad_() if v.is_floating_point() and v.dim() > 0 and "scale_factor" not in k
+def _oracle_grads(weights, b, G1, G2, dtype=torch.float64):
+    P = {k: (v.to(dtype).clone().requires_grad_() if v.is_floating_point() and v.dim() > 0 and "scale_factor" not in k
              and "atom_radii" not in k else v) for k, v in weights.items()}
-    o1, o2 = O.painn_forward(P, b.atomic_numbers.numpy(), b.pos.numpy(), b.cell.numpy(), b.natoms, dtype=torch.float64)
-    ((o1 * G1.double()).sum() + (o2 * G2.double()).sum()).backward()
+    o1, o2 = O.painn_forward(P, b.atomic_numbers.numpy(), b.pos.numpy(), b.cell.numpy(), b.natoms, dtype=dtype)
+    ((o1 * G1.to(dtype)).sum() + (o2 * G2.to(dtype)).sum()).backward()
     return P, o1.detach(), o2.detach()
 
 
 @pytest.mark.parametrize("name", ["tiny", "jit2"])
-def test_parameter_gradients_match_fp64_oracle(name, net, weights):
+def test_backward_matches_oracle(name, net, weights):
     b = CASES[name][0]()
     g = torch.Generator().manual_seed(1)
     G1, G2 = torch.randn(b.pos.shape[0], 3, generator=g), torch.randn(b.pos.shape[0], 3, generator=g)
     P, o1, o2 = _oracle_grads(weights, b, G1, G2)
+    P32, _, _ = _oracle_grads(weights, b, G1, G2, dtype=torch.float32)
     net.train()
     f1, f2 = net(b.to("cuda:0"))
     assert f1.requires_grad and f2.requires_grad
     for got, want in ((f1, o1), (f2, o2)):
         assert (got.detach().cpu().double() - want).abs().max() <= 1e-5 * want.abs().max()
     ((f1 * G1.cuda()).sum() + (f2 * G2.cuda()).sum()).backward()
-    worst = ("", 0.0)
+    worst, worst32 = ("", 0.0), ("", 0.0)
     checked = 0
     for k, q in net.named_parameters():
         if not q.requires_grad:
@@ -58,11 +60,15 @@ def test_parameter_gradients_match_fp64_oracle(name, net, weights):
             continue
         assert q.grad is not None, k
         err = float((q.grad.cpu().double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        err32 = float((P32[k].grad.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
         if err > worst[1]:
             worst = (k, err)
+        if err32 > worst32[1]:
+            worst32 = (k, err32)
         checked += 1
-    print(f"{name}: {checked} gradients, worst {worst[0]} {worst[1]:.2e}")
-    assert checked >= 60 and worst[1] <= GRAD_TOL, worst
+    print(f"{name}: {checked} gradients; cuda-vs-fp64 worst {worst[0]} {worst[1]:.2e}; "
+          f"fp32 torch autograd (CPU oracle)-vs-fp64 worst {worst32[0]} {worst32[1]:.2e}")
+    assert checked >= 60 and worst[1] <= GRAD_TOL and worst[1] <= 2 * max(worst32[1], 5e-6), (worst, worst32)
 
 
 def test_message_backward_alone(net):
@@ -71,6 +77,10 @@ def test_message_backward_alone(net):
     p, z, pos = net._prepare(b)
     net._graph(p, pos)
     net.check_status(p)
+    from adsorbdiff_b200 import _cabi
+    p.bwd_plan = torch.empty(_cabi.load().adk_message_bwd_plan_ints(p.N, p.e_src.numel()), dtype=torch.int32, device="cuda")
+    _cabi.call("adk_message_bwd_plan", p.device, _cabi.ptr(p.row_start), _cabi.ptr(p.row_deg), _cabi.ptr(p.e_src),
+               _cabi.ptr(p.e_geo), p.N, net.num_rbf, float(net.cutoff), net.radial_basis.exponent, _cabi.ptr(p.bwd_plan))
     N, F_, R = p.N, net.hidden_channels, net.num_rbf
     g = torch.Generator(device="cuda").manual_seed(3)
     mk = lambda *s: torch.randn(*s, device="cuda", generator=g)
