@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB_DIR = os.path.join(os.path.dirname(HERE), "lib")
 LIB = os.path.join(LIB_DIR, "libadsorbdiff_b200.so")
-SOURCES = ["api.cu", "neighbors.cu", "node_ops.cu", "linear.cu", "linear_tc.cu", "message.cu", "message_t5.cu", "message_mma.cu", "message_bwd.cu", "se3_step.cu"]
+SOURCES = ["api.cu", "neighbors.cu", "node_ops.cu", "linear.cu", "linear_tc.cu", "message.cu", "message_t5.cu", "message_mma.cu", "message_bwd.cu", "train_ops.cu", "se3_step.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + HERE,

@@ -88,6 +88,8 @@ struct TcParams {
     int w_lo_row;   // same for W (= N)
     const float* bias;
     float acc_scale;
+    const float* sa_rec;   // optional device records {s, 1/s} of the two operands' prescales (adk_linear_tc_dev):
+    const float* sb_rec;   // acc_scale = sa_rec[1] * sb_rec[1]
     float gain0, gain1;
     int act;
     float* out_f32;
@@ -260,6 +262,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;               // TMEM lane quarter this warp may access
         const int half = (warp - TC_EPI_WARP0) >> 2;     // which column half of the accumulator it owns
         const int num_chunks = (num_k + TC_PROMOTE - 1) / TC_PROMOTE;
+        const float acc_scale = P.sa_rec ? P.sa_rec[1] * P.sb_rec[1] : P.acc_scale;
         int astage = 0;
         uint32_t aphase = 0;
         bool overflow = false;
@@ -313,7 +316,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        const float t = fmaf(acc[pc * 16 + 4 * j4 + jj], P.acc_scale, bb[jj]);
+                        const float t = fmaf(acc[pc * 16 + 4 * j4 + jj], acc_scale, bb[jj]);
                         o[4 * j4 + jj] = (ACT == ADK_ACT_SSILU) ? ssilu_fast(t) : t;
                     }
                 }
@@ -448,10 +451,10 @@ extern "C" int adk_set_tc_pair(int enable) {
     return 0;
 }
 
-extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, const void* w_split, int N, int K,
-                             const float* bias, float acc_scale, int act, float* out_f32, int64_t ldc,
-                             void* out_split, int64_t out_plane_rows, float out_split_scale, uint32_t* status,
-                             void* stream) {
+static int linear_tc_launch(const void* a_split, int64_t a_plane_rows, int M, const void* w_split, int N, int K,
+                            const float* bias, float acc_scale, const float* sa_rec, const float* sb_rec, int act,
+                            float* out_f32, int64_t ldc, void* out_split, int64_t out_plane_rows, float out_split_scale,
+                            uint32_t* status, void* stream) {
     if (!a_split || !w_split || M <= 0 || N <= 0 || K <= 0 || (!out_f32 && !out_split)) return ADK_EINVAL;
     if (N % 16 != 0 || K % TC_BK != 0 || a_plane_rows < M || a_plane_rows % TC_BM != 0) return ADK_EINVAL;
     if (out_f32 && ((ldc & 3) || (reinterpret_cast<uintptr_t>(out_f32) & 15))) return ADK_EINVAL;
@@ -470,6 +473,7 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     P.M = M; P.N = N; P.K = K;
     P.a_lo_row = (int)a_plane_rows; P.w_lo_row = N;
     P.bias = bias; P.acc_scale = acc_scale; P.act = act;
+    P.sa_rec = sa_rec; P.sb_rec = sb_rec;
     P.gain0 = g_tc_gain[0]; P.gain1 = g_tc_gain[1];
     P.out_f32 = out_f32; P.ldc = ldc;
     P.out_split = reinterpret_cast<__half*>(out_split);
@@ -526,6 +530,23 @@ extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, c
     if (le != cudaSuccess) return (int)le;
     ADK_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, const void* w_split, int N, int K,
+                             const float* bias, float acc_scale, int act, float* out_f32, int64_t ldc,
+                             void* out_split, int64_t out_plane_rows, float out_split_scale, uint32_t* status,
+                             void* stream) {
+    return linear_tc_launch(a_split, a_plane_rows, M, w_split, N, K, bias, acc_scale, nullptr, nullptr, act, out_f32, ldc,
+                            out_split, out_plane_rows, out_split_scale, status, stream);
+}
+
+// the same GEMM with the operands' prescales taken from device records (csrc/train_ops.cu): C = A . W^T / (s_A s_W) + bias
+extern "C" int adk_linear_tc_dev(const void* a_split, int64_t a_plane_rows, int M, const void* w_split, int N, int K,
+                                 const float* bias, const float* sa_rec, const float* sb_rec, float* out_f32, int64_t ldc,
+                                 uint32_t* status, void* stream) {
+    if (!sa_rec || !sb_rec || !out_f32) return ADK_EINVAL;
+    return linear_tc_launch(a_split, a_plane_rows, M, w_split, N, K, bias, 1.0f, sa_rec, sb_rec, ADK_ACT_NONE, out_f32, ldc,
+                            nullptr, 0, 1.0f, status, stream);
 }
 
 namespace adk { namespace tc {

@@ -1,0 +1,138 @@
+// Operand preparation for the tensor-core GEMMs of the TRAINING step.
+//
+// The sampling path measures its fp16x2 prescales once (PaiNN.calibrate) and passes them by value.  Gradients have no
+// stable range, so here every GEMM operand gets its prescale on the device, per call, with no host round trip:
+//   adk_amax_scale          rec = {s, 1/s}, s = the power of two that puts max|x| into [target/2, target]
+//   adk_split_f16_dev       fp32 [M][K]  -> fp16x2 planes [2][plane_rows][K]       scaled by rec[0], pad rows zeroed
+//   adk_split_f16_t_dev     fp32 [M][C]  -> planes of the TRANSPOSE [2][plane_rows][Kp] (Kp >= M), pads zeroed
+// and adk_linear_tc_dev (csrc/linear_tc.cu) undoes the two scales in its epilogue from the same records.  Together
+// they give  Y = X W^T,  dX = dY W,  dW = dY^T X  (torch.nn.Linear forward / backward, reference:
+// models/painn/painn_denoising.py:508-512, 580-587, 667-676 under torch autograd) on tcgen05 at fp32 parity.
+// Powers of two only: scaling and unscaling are exact.
+#include "common.cuh"
+
+namespace {
+
+// scratch[0] = running max of |x| as float bits (non-negative floats order like unsigned ints), scratch[1] = blocks done
+__global__ void amax_scale_kernel(const float* __restrict__ src, int64_t n, float target, float* __restrict__ rec,
+                                  unsigned int* __restrict__ scratch) {
+    float m = 0.f;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(src[(n4 << 2) + threadIdx.x]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(ADK_FULL_MASK, m, o));
+    __shared__ float s_m[8];
+    __shared__ bool s_last;
+    if (adk::lane_id() == 0) s_m[adk::warp_id()] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_m[w]);
+        if (!(m <= 3.0e38f)) m = 3.0e38f;   // inf / nan: the split will raise the overflow bit
+        atomicMax(&scratch[0], __float_as_uint(m));
+        __threadfence();
+        s_last = atomicAdd(&scratch[1], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const float amax = __uint_as_float(atomicMax(&scratch[0], 0u));
+        float s = 1.0f;
+        if (amax > 0.f) {
+            int e;
+            frexpf(target / amax, &e);      // target / amax = f * 2^e, f in [0.5, 1)  ->  2^(e-1) <= target / amax
+            e = max(-100, min(100, e - 1));
+            s = ldexpf(1.0f, e);
+        }
+        rec[0] = s;
+        rec[1] = 1.0f / s;
+        scratch[0] = 0u;                      // ready for the next call on this scratch
+        scratch[1] = 0u;
+    }
+}
+
+__device__ __forceinline__ void split4(float4 v, float scale, uint2& hi2, uint2& lo2, bool& overflow) {
+    __align__(8) __half hi[4];
+    __align__(8) __half lo[4];
+    adk::split_f16x2(v.x, scale, hi[0], lo[0], overflow);
+    adk::split_f16x2(v.y, scale, hi[1], lo[1], overflow);
+    adk::split_f16x2(v.z, scale, hi[2], lo[2], overflow);
+    adk::split_f16x2(v.w, scale, hi[3], lo[3], overflow);
+    hi2 = *reinterpret_cast<const uint2*>(hi);
+    lo2 = *reinterpret_cast<const uint2*>(lo);
+}
+
+// one thread per 4 consecutive k of one (possibly padding) row
+__global__ void split_dev_kernel(const float* __restrict__ src, int64_t ld, int M, int K, const float* __restrict__ rec,
+                                 __half* __restrict__ dst, int64_t plane_rows, uint32_t* status) {
+    const int K4 = K >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plane_rows * K4) return;
+    const int64_t m = idx / K4;
+    const int k4 = (int)(idx - m * K4);
+    uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
+    bool overflow = false;
+    if (m < M) split4(*reinterpret_cast<const float4*>(src + m * ld + 4 * k4), rec[0], hi, lo, overflow);
+    *reinterpret_cast<uint2*>(dst + m * K + 4 * k4) = hi;
+    *reinterpret_cast<uint2*>(dst + plane_rows * K + m * K + 4 * k4) = lo;
+    if (overflow && status) atomicOr(status, ADK_STATUS_F16_OVERFLOW);
+}
+
+// dst[c][m] = split(src[m][c]) through a 32 x 33 tile; grid (Kp / 32, plane_rows / 32), 256 threads
+__global__ void split_t_dev_kernel(const float* __restrict__ src, int64_t ld, int M, int C, const float* __restrict__ rec,
+                                   __half* __restrict__ dst, int64_t plane_rows, int64_t Kp, uint32_t* status) {
+    __shared__ float tile[32][33];
+    const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows per pass
+    for (int r = ty; r < 32; r += 8) {
+        const int m = m0 + r, c = c0 + tx;
+        tile[r][tx] = (m < M && c < C) ? src[(int64_t)m * ld + c] : 0.f;
+    }
+    __syncthreads();
+    const float scale = rec[0];
+    bool overflow = false;
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t c = c0 + r, m = m0 + tx;
+        if (c < plane_rows && m < Kp) {
+            __half h, l;
+            adk::split_f16x2(tile[tx][r], scale, h, l, overflow);
+            dst[c * Kp + m] = h;
+            dst[plane_rows * Kp + c * Kp + m] = l;
+        }
+    }
+    if (overflow && status) atomicOr(status, ADK_STATUS_F16_OVERFLOW);
+}
+
+}  // namespace
+
+extern "C" int adk_amax_scale(const float* src, int64_t n, float target, float* rec, uint32_t* scratch, void* stream) {
+    if (!src || !rec || !scratch || n <= 0 || !(target > 0.f) || (reinterpret_cast<uintptr_t>(src) & 15)) return ADK_EINVAL;
+    int64_t blocks = (n / 4 + 255) / 256;
+    blocks = blocks < 1 ? 1 : (blocks > 592 ? 592 : blocks);
+    amax_scale_kernel<<<(unsigned)blocks, 256, 0, adk::as_stream(stream)>>>(src, n, target, rec, scratch);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int adk_split_f16_dev(const float* src, int64_t ld, int M, int K, const float* rec, void* dst,
+                                 int64_t plane_rows, uint32_t* status, void* stream) {
+    if (!src || !dst || !rec || M <= 0 || K <= 0 || (K & 3) || (ld & 3) || plane_rows < M) return ADK_EINVAL;
+    const int64_t n = plane_rows * (K >> 2);
+    split_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, adk::as_stream(stream)>>>(
+        src, ld, M, K, rec, reinterpret_cast<__half*>(dst), plane_rows, status);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int adk_split_f16_t_dev(const float* src, int64_t ld, int M, int C, const float* rec, void* dst,
+                                   int64_t plane_rows, int64_t Kp, uint32_t* status, void* stream) {
+    if (!src || !dst || !rec || M <= 0 || C <= 0 || plane_rows < C || Kp < M || ld < C) return ADK_EINVAL;
+    dim3 grid((unsigned)((Kp + 31) / 32), (unsigned)((plane_rows + 31) / 32));
+    split_t_dev_kernel<<<grid, 256, 0, adk::as_stream(stream)>>>(src, ld, M, C, rec, reinterpret_cast<__half*>(dst),
+                                                                 plane_rows, Kp, status);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}

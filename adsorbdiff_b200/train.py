@@ -78,20 +78,134 @@ class MessageFn(torch.autograd.Function):
         return g_dx, grad_vec, d_xh, d_w, d_b, None, None
 
 
+# --------------------------------------------------------------------------------------------------------------
+# nn.Linear forward / backward on the tcgen05 GEMM (csrc/linear_tc.cu) with device-side prescales (csrc/train_ops.cu)
+# --------------------------------------------------------------------------------------------------------------
+SPLIT_TARGET = 2048.0    # scaled magnitudes are placed in [1024, 2048]: 32x below the fp16 limit
+
+
+def _pad(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+class _TcWorkspace:
+    """Per-device scratch of the training GEMMs: the amax kernel's two counters and an overflow status word."""
+
+    def __init__(self, device):
+        self.device = device
+        self.scratch = torch.zeros(2, dtype=torch.int32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+
+    _by_device: dict = {}
+
+    @classmethod
+    def get(cls, device) -> "_TcWorkspace":
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        ws = cls._by_device.get(key)
+        if ws is None:
+            ws = cls._by_device[key] = cls(torch.device("cuda", key[1]))
+        return ws
+
+
+def _rec(t: torch.Tensor, ws: _TcWorkspace) -> torch.Tensor:
+    """{s, 1/s}: the power-of-two prescale of `t`, computed on the device (no host sync)."""
+    rec = torch.empty(2, dtype=torch.float32, device=t.device)
+    call("adk_amax_scale", ws.device, ptr(t), t.numel(), SPLIT_TARGET, ptr(rec), ptr(ws.scratch))
+    return rec
+
+
+def _split(t: torch.Tensor, rec, ws, plane_rows: int) -> torch.Tensor:
+    M, K = t.shape
+    out = torch.empty(2 * plane_rows * K, dtype=torch.float16, device=t.device)
+    call("adk_split_f16_dev", ws.device, ptr(t), K, M, K, ptr(rec), ptr(out), plane_rows, ptr(ws.status))
+    return out
+
+
+def _split_t(t: torch.Tensor, rec, ws, plane_rows: int, kp: int) -> torch.Tensor:
+    M, C = t.shape
+    out = torch.empty(2 * plane_rows * kp, dtype=torch.float16, device=t.device)
+    call("adk_split_f16_t_dev", ws.device, ptr(t), C, M, C, ptr(rec), ptr(out), plane_rows, kp, ptr(ws.status))
+    return out
+
+
+def _gemm_nt(a, a_rows: int, M: int, w, N: int, K: int, bias, rec_a, rec_w, ws) -> torch.Tensor:
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    call("adk_linear_tc_dev", ws.device, ptr(a), a_rows, M, ptr(w), N, K, ptr(bias) if bias is not None else None,
+         ptr(rec_a), ptr(rec_w), ptr(out), N, ptr(ws.status))
+    return out
+
+
+def _aligned(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous and 16-byte aligned (the kernels read float4)."""
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+class TcLinearFn(torch.autograd.Function):
+    """y = x W^T + b with all three GEMMs (Y, dX = dY W, dW = dY^T X) on the tcgen05 fp16x2-split kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ws = _TcWorkspace.get(x.device)
+        x, w = _aligned(x.detach()), _aligned(w.detach())
+        M, K = x.shape
+        N = w.shape[0]
+        rx, rw = _rec(x, ws), _rec(w, ws)
+        mp = _pad(M, 128)
+        y = _gemm_nt(_split(x, rx, ws, mp), mp, M, _split(w, rw, ws, N), N, K,
+                     b.detach().contiguous() if b is not None else None, rx, rw, ws)
+        ctx.save_for_backward(x, w, rx, rw)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, rx, rw = ctx.saved_tensors
+        ws = _TcWorkspace.get(x.device)
+        g = _aligned(g)
+        M, K = x.shape
+        N = w.shape[0]
+        rg = _rec(g, ws)
+        mp, kred = _pad(M, 128), _pad(M, 64)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:      # dX[M,K] = dY[M,N] . (W^T)[K,N]^T
+            dx = _gemm_nt(_split(g, rg, ws, mp), mp, M, _split_t(w, rw, ws, K, N), K, N, None, rg, rw, ws)
+        if ctx.needs_input_grad[1]:      # dW[N,K] = (dY^T)[N,M] . (X^T)[K,M]^T
+            np_ = _pad(N, 128)
+            dw = _gemm_nt(_split_t(g, rg, ws, np_, kred), np_, N, _split_t(x, rx, ws, K, kred), K, kred, None, rg, rx, ws)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = g.sum(0)
+        return dx, dw, db
+
+
+def _tc_shape_ok(lin) -> bool:
+    n, k = lin.weight.shape
+    return k % 64 == 0 and n % 64 == 0 and n <= 2048 and k <= 2048
+
+
+def _lin(net, lin, x):
+    """`lin(x)`: on the tensor-core GEMM when `net.train_gemm == "tc"` and the shape allows, else torch (cuBLAS fp32)."""
+    if getattr(net, "train_gemm", "tc") != "tc" or not _tc_shape_ok(lin):
+        return lin(x)
+    lead = x.shape[:-1]
+    y = TcLinearFn.apply(x.reshape(-1, x.shape[-1]), lin.weight, lin.bias)
+    return y.reshape(*lead, y.shape[-1])
+
+
 def _ssilu(x):
     """ScaledSiLU (gemnet_oc/layers/base_layers.py:65-72)"""
     return F.silu(x) * (1.0 / 0.6)
 
 
-def _mlp(seq, x):
-    return seq[2](_ssilu(seq[0](x)))
+def _mlp(net, seq, x):
+    return _lin(net, seq[2], _ssilu(_lin(net, seq[0], x)))
 
 
-def _gated_block(blk, x, v, out_channels: int):
+def _gated_block(net, blk, x, v, out_channels: int):
     """GatedEquivariantBlock.forward (painn_denoising.py:688-697)"""
-    vec1 = torch.norm(blk.vec1_proj(v), dim=-2)
-    vec2 = blk.vec2_proj(v)
-    h = _mlp(blk.update_net, torch.cat([x, vec1], dim=-1))
+    vec1 = torch.norm(_lin(net, blk.vec1_proj, v), dim=-2)
+    vec2 = _lin(net, blk.vec2_proj, v)
+    h = _mlp(net, blk.update_net, torch.cat([x, vec1], dim=-1))
     xo, g = torch.split(h, out_channels, dim=-1)
     return _ssilu(xo), g.unsqueeze(1) * vec2
 
@@ -140,11 +254,11 @@ def forward_train(net, data, check: bool = True):
     vec = None
     for l in range(net.num_layers):
         m, u = net.message_layers[l], net.update_layers[l]
-        xh = _mlp(m.x_proj, m.x_layernorm(x))
+        xh = _mlp(net, m.x_proj, m.x_layernorm(x))
         x, vec = MessageFn.apply(x, vec, xh, m.rbf_proj.weight, m.rbf_proj.bias, net, p)
-        v1, v2 = torch.split(u.vec_proj(vec), F_, dim=-1)
+        v1, v2 = torch.split(_lin(net, u.vec_proj, vec), F_, dim=-1)
         vec_dot = (v1 * v2).sum(dim=1) * (1.0 / math.sqrt(F_))
-        h = _mlp(u.xvec_proj, torch.cat([x, torch.sqrt(torch.sum(v2 ** 2, dim=-2) + 1e-8)], dim=-1))
+        h = _mlp(net, u.xvec_proj, torch.cat([x, torch.sqrt(torch.sum(v2 ** 2, dim=-2) + 1e-8)], dim=-1))
         a, bq, c = torch.split(h, F_, dim=-1)
         x = x + (a + bq * vec_dot) * INV_SQRT_2
         vec = vec + c.unsqueeze(1) * v1
@@ -152,8 +266,8 @@ def forward_train(net, data, check: bool = True):
         x = torch.where(sc != 0.0, x * sc, x)   # ScaleFactor.forward multiplies only when fitted (no host sync here)
     outs = []
     for head in ([net.out_forces, net.out_forces2] if net.so3_denoising else [net.out_forces]):
-        hx, hv = _gated_block(head.output_network[0], x, vec, F_ // 2)
-        hx, hv = _gated_block(head.output_network[1], hx, hv, 1)
+        hx, hv = _gated_block(net, head.output_network[0], x, vec, F_ // 2)
+        hx, hv = _gated_block(net, head.output_network[1], hx, hv, 1)
         outs.append(hv.squeeze(-1))
     net._train_plan = p
     if check:

@@ -133,6 +133,25 @@ int adk_linear(const float* A, int64_t lda, const float* W, const float* bias, i
  */
 int adk_split_f16(const float* src, int64_t ld, int M, int K, float scale, void* dst, int64_t plane_rows,
                   uint32_t* status, void* stream);
+/*
+ * Training-side operand preparation (csrc/train_ops.cu): prescales found on the device, per call, no host round trip.
+ *   adk_amax_scale:     rec[0] = s, rec[1] = 1/s with s the power of two that puts max|src| into [target/2, target]
+ *                       (s = 1 for an all-zero tensor); scratch = 2 zero-initialised uint32 (left zeroed again)
+ *   adk_split_f16_dev:  adk_split_f16 with the scale read from rec[0]; rows [M, plane_rows) are written as zeros
+ *   adk_split_f16_t_dev: planes of the TRANSPOSE of src[M][C] (row stride ld): dst [2][plane_rows][Kp], dst[c][m] =
+ *                       split(src[m][c]), zeros for c >= C or m >= M (Kp >= M: the reduction length of the GEMM, a
+ *                       multiple of 64; plane_rows >= C)
+ *   adk_linear_tc_dev:  out_f32[M][ldc] = A . W^T * sa_rec[1] * sb_rec[1] + bias (bias may be NULL); operand layout
+ *                       as for adk_linear_tc.  With these: Y = X W^T, dX = dY W, dW = dY^T X of torch.nn.Linear.
+ */
+int adk_amax_scale(const float* src, int64_t n, float target, float* rec, uint32_t* scratch, void* stream);
+int adk_split_f16_dev(const float* src, int64_t ld, int M, int K, const float* rec, void* dst, int64_t plane_rows,
+                      uint32_t* status, void* stream);
+int adk_split_f16_t_dev(const float* src, int64_t ld, int M, int C, const float* rec, void* dst, int64_t plane_rows,
+                        int64_t Kp, uint32_t* status, void* stream);
+int adk_linear_tc_dev(const void* a_split, int64_t a_plane_rows, int M, const void* w_split, int N, int K,
+                      const float* bias, const float* sa_rec, const float* sb_rec, float* out_f32, int64_t ldc,
+                      uint32_t* status, void* stream);
 /* Tuning knob: run wide GEMMs as cta_group::2 CTA pairs (one MMA over M = 256 rows, each CTA staging half of the
  * weight tile).  On by default (5 % faster at two k-blocks per promotion, bit-identical results; see csrc/linear_tc.cu);
  * ADK_TC_PAIR=0 in the environment also turns it off. */

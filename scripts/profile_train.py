@@ -20,3 +20,14 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step(hosts[i % 2].clone())
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=35, max_name_column_width=70))
+
+# host enqueue time of one step (no sync inside: TrainStep reads nothing back)
+import time
+torch.cuda.synchronize()
+ts = []
+for i in range(6):
+    t0 = time.perf_counter()
+    loss = step(hosts[i % 2].clone())
+    ts.append(time.perf_counter() - t0)
+torch.cuda.synchronize()
+print("host enqueue ms per step:", [f"{1e3 * t:.1f}" for t in ts])

@@ -36,8 +36,12 @@ def _oracle_grads(weights, b, G1, G2, dtype=torch.float64):
     return P, o1.detach(), o2.detach()
 
 
+@pytest.mark.parametrize("gemm", ["tc", "torch"])
 @pytest.mark.parametrize("name", ["tiny", "jit2"])
-def test_backward_matches_oracle(name, net, weights):
+def test_backward_matches_oracle(name, gemm, net, weights):
+    """`gemm`: the nn.Linear layers' three GEMMs on the tcgen05 kernel with device-side prescales ("tc", the default)
+    or on cuBLAS fp32 through torch ("torch")."""
+    net.train_gemm = gemm
     b = CASES[name][0]()
     g = torch.Generator().manual_seed(1)
     G1, G2 = torch.randn(b.pos.shape[0], 3, generator=g), torch.randn(b.pos.shape[0], 3, generator=g)
@@ -66,9 +70,30 @@ def test_backward_matches_oracle(name, net, weights):
         if err32 > worst32[1]:
             worst32 = (k, err32)
         checked += 1
-    print(f"{name}: {checked} gradients; cuda-vs-fp64 worst {worst[0]} {worst[1]:.2e}; "
+    print(f"{name}/{gemm}: {checked} gradients; cuda-vs-fp64 worst {worst[0]} {worst[1]:.2e}; "
           f"fp32 torch autograd (CPU oracle)-vs-fp64 worst {worst32[0]} {worst32[1]:.2e}")
     assert checked >= 60 and worst[1] <= GRAD_TOL and worst[1] <= 2 * max(worst32[1], 5e-6), (worst, worst32)
+
+
+@pytest.mark.parametrize("M,K,N", [(300, 512, 1536), (77, 1024, 512), (1000, 256, 256), (12345, 512, 1024)])
+def test_tc_linear_forward_backward(M, K, N):
+    """TcLinearFn (Y, dX, dW on the tcgen05 GEMM, prescales from device amax) against fp64, operands of very different
+    magnitudes (gradients are not O(1)): each result within 2e-6 of its own max."""
+    g = torch.Generator(device="cuda").manual_seed(M)
+    x = (torch.randn(M, K, device="cuda", generator=g) * 37.0).requires_grad_()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.003).requires_grad_()
+    b = torch.randn(N, device="cuda", generator=g).requires_grad_()
+    G = torch.randn(M, N, device="cuda", generator=g) * 1e-4
+    y = T.TcLinearFn.apply(x, w, b)
+    (y * G).sum().backward()
+    x6, w6, b6 = (t.detach().double().requires_grad_() for t in (x, w, b))
+    y6 = x6 @ w6.T + b6
+    (y6 * G.double()).sum().backward()
+    for name, a, r in (("y", y, y6), ("dx", x.grad, x6.grad), ("dw", w.grad, w6.grad), ("db", b.grad, b6.grad)):
+        err = float((a.double() - r).abs().max() / r.abs().max())
+        print(f"M={M} K={K} N={N} {name}: {err:.2e}")
+        assert err <= 2e-6, (name, err)
+    assert int(T._TcWorkspace.get(x.device).status.item()) == 0
 
 
 def test_message_backward_alone(net):
