@@ -136,3 +136,65 @@ extern "C" int adk_split_f16_t_dev(const float* src, int64_t ld, int M, int C, c
     ADK_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- one call per nn.Linear pass (host-side fusion: the launches below are what `TcLinearFn` used to issue one ctypes
+// call at a time; at ~40 Linear layers per step that was 7 ms of Python per training step) ------------------------
+namespace {
+inline int64_t pad_to(int64_t n, int64_t m) { return (n + m - 1) / m * m; }
+inline uint8_t* carve(uint8_t*& p, int64_t bytes) {
+    uint8_t* r = p;
+    p += (bytes + 255) / 256 * 256;
+    return r;
+}
+}  // namespace
+
+extern "C" int64_t adk_linear_train_ws_bytes(int M, int K, int N) {
+    if (M <= 0 || K <= 0 || N <= 0) return ADK_EINVAL;
+    const int64_t mp = pad_to(M, 128), np = pad_to(N, 128), kred = pad_to(M, 64);
+    auto planes = [](int64_t rows, int64_t cols) { return (2 * rows * cols * 2 + 255) / 256 * 256; };
+    const int64_t fwd = planes(mp, K) + planes(N, K);
+    const int64_t bwd = planes(mp, N) + planes(K, N) + planes(np, kred) + planes(K, kred);
+    return (fwd > bwd ? fwd : bwd) + 256;
+}
+
+// y[M][N] = x[M][K] . w[N][K]^T + bias;  recs[4] <- {s_x, 1/s_x, s_w, 1/s_w} (kept by the caller for the backward)
+extern "C" int adk_linear_train_fwd(const float* x, const float* w, const float* bias, int M, int K, int N, float target,
+                                    float* recs, void* ws, uint32_t* scratch, uint32_t* status, float* y, void* stream) {
+    if (!x || !w || !recs || !ws || !scratch || !y) return ADK_EINVAL;
+    const int64_t mp = pad_to(M, 128);
+    uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+    void* xa = carve(p, 2 * mp * K * 2);
+    void* wa = carve(p, 2 * (int64_t)N * K * 2);
+    int rc;
+    if ((rc = adk_amax_scale(x, (int64_t)M * K, target, recs, scratch, stream)) != 0) return rc;
+    if ((rc = adk_amax_scale(w, (int64_t)N * K, target, recs + 2, scratch, stream)) != 0) return rc;
+    if ((rc = adk_split_f16_dev(x, K, M, K, recs, xa, mp, status, stream)) != 0) return rc;
+    if ((rc = adk_split_f16_dev(w, K, N, K, recs + 2, wa, N, status, stream)) != 0) return rc;
+    return adk_linear_tc_dev(xa, mp, M, wa, N, K, bias, recs, recs + 2, y, N, status, stream);
+}
+
+// dx[M][K] = g[M][N] . w[N][K]  (if dx)   and   dw[N][K] = g[M][N]^T . x[M][K]  (if dw);  recs from the forward
+extern "C" int adk_linear_train_bwd(const float* g, const float* x, const float* w, int M, int K, int N, float target,
+                                    const float* recs, float* rec_g, void* ws, uint32_t* scratch, uint32_t* status,
+                                    float* dx, float* dw, void* stream) {
+    if (!g || !x || !w || !recs || !rec_g || !ws || !scratch) return ADK_EINVAL;
+    const int64_t mp = pad_to(M, 128), np = pad_to(N, 128), kred = pad_to(M, 64);
+    uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+    int rc;
+    if ((rc = adk_amax_scale(g, (int64_t)M * N, target, rec_g, scratch, stream)) != 0) return rc;
+    if (dx) {
+        void* ga = carve(p, 2 * mp * N * 2);
+        void* wt = carve(p, 2 * (int64_t)K * N * 2);
+        if ((rc = adk_split_f16_dev(g, N, M, N, rec_g, ga, mp, status, stream)) != 0) return rc;
+        if ((rc = adk_split_f16_t_dev(w, K, N, K, recs + 2, wt, K, N, status, stream)) != 0) return rc;
+        if ((rc = adk_linear_tc_dev(ga, mp, M, wt, K, N, nullptr, rec_g, recs + 2, dx, K, status, stream)) != 0) return rc;
+    }
+    if (dw) {
+        void* gt = carve(p, 2 * np * kred * 2);
+        void* xt = carve(p, 2 * (int64_t)K * kred * 2);
+        if ((rc = adk_split_f16_t_dev(g, N, M, N, rec_g, gt, np, kred, status, stream)) != 0) return rc;
+        if ((rc = adk_split_f16_t_dev(x, K, M, K, recs, xt, K, kred, status, stream)) != 0) return rc;
+        if ((rc = adk_linear_tc_dev(gt, np, N, xt, K, (int)kred, nullptr, rec_g, recs, dw, K, status, stream)) != 0) return rc;
+    }
+    return 0;
+}

@@ -95,6 +95,17 @@ class _TcWorkspace:
         self.device = device
         self.scratch = torch.zeros(2, dtype=torch.int32, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.planes = torch.empty(0, dtype=torch.uint8, device=device)
+        self.rec_g = torch.empty(2, dtype=torch.float32, device=device)
+
+    def operand_space(self, M: int, K: int, N: int) -> torch.Tensor:
+        """Device scratch for the operand planes of one Linear pass (grown on demand; stream-ordered reuse)."""
+        # = adk_linear_train_ws_bytes(M, K, N), evaluated here (this runs ~80 times per step)
+        mp, np_, kr = _pad(M, 128), _pad(N, 128), _pad(M, 64)
+        need = 4 * max(mp * K + N * K, mp * N + K * N + np_ * kr + K * kr) + 2048
+        if self.planes.numel() < need:
+            self.planes = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
+        return self.planes
 
     _by_device: dict = {}
 
@@ -142,7 +153,8 @@ def _aligned(t: torch.Tensor) -> torch.Tensor:
 
 
 class TcLinearFn(torch.autograd.Function):
-    """y = x W^T + b with all three GEMMs (Y, dX = dY W, dW = dY^T X) on the tcgen05 fp16x2-split kernel."""
+    """y = x W^T + b with all three GEMMs (Y, dX = dY W, dW = dY^T X) on the tcgen05 fp16x2-split kernel; one C call
+    per pass (`adk_linear_train_fwd` / `_bwd`: device amax -> power-of-two prescale -> split -> GEMM)."""
 
     @staticmethod
     def forward(ctx, x, w, b):
@@ -150,31 +162,26 @@ class TcLinearFn(torch.autograd.Function):
         x, w = _aligned(x.detach()), _aligned(w.detach())
         M, K = x.shape
         N = w.shape[0]
-        rx, rw = _rec(x, ws), _rec(w, ws)
-        mp = _pad(M, 128)
-        y = _gemm_nt(_split(x, rx, ws, mp), mp, M, _split(w, rw, ws, N), N, K,
-                     b.detach().contiguous() if b is not None else None, rx, rw, ws)
-        ctx.save_for_backward(x, w, rx, rw)
+        recs = torch.empty(4, dtype=torch.float32, device=x.device)
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        call("adk_linear_train_fwd", ws.device, ptr(x), ptr(w), ptr(_aligned(b.detach())) if b is not None else None, M, K, N,
+             SPLIT_TARGET, ptr(recs), ptr(ws.operand_space(M, K, N)), ptr(ws.scratch), ptr(ws.status), ptr(y))
+        ctx.save_for_backward(x, w, recs)
         ctx.has_bias = b is not None
         return y
 
     @staticmethod
     def backward(ctx, g):
-        x, w, rx, rw = ctx.saved_tensors
+        x, w, recs = ctx.saved_tensors
         ws = _TcWorkspace.get(x.device)
         g = _aligned(g)
         M, K = x.shape
         N = w.shape[0]
-        rg = _rec(g, ws)
-        mp, kred = _pad(M, 128), _pad(M, 64)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:      # dX[M,K] = dY[M,N] . (W^T)[K,N]^T
-            dx = _gemm_nt(_split(g, rg, ws, mp), mp, M, _split_t(w, rw, ws, K, N), K, N, None, rg, rw, ws)
-        if ctx.needs_input_grad[1]:      # dW[N,K] = (dY^T)[N,M] . (X^T)[K,M]^T
-            np_ = _pad(N, 128)
-            dw = _gemm_nt(_split_t(g, rg, ws, np_, kred), np_, N, _split_t(x, rx, ws, K, kred), K, kred, None, rg, rx, ws)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = g.sum(0)
+        dx = torch.empty(M, K, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        dw = torch.empty(N, K, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[1] else None
+        call("adk_linear_train_bwd", ws.device, ptr(g), ptr(x), ptr(w), M, K, N, SPLIT_TARGET, ptr(recs), ptr(ws.rec_g),
+             ptr(ws.operand_space(M, K, N)), ptr(ws.scratch), ptr(ws.status), ptr(dx), ptr(dw))
+        db = g.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dw, db
 
 

@@ -152,6 +152,19 @@ int adk_split_f16_t_dev(const float* src, int64_t ld, int M, int C, const float*
 int adk_linear_tc_dev(const void* a_split, int64_t a_plane_rows, int M, const void* w_split, int N, int K,
                       const float* bias, const float* sa_rec, const float* sb_rec, float* out_f32, int64_t ldc,
                       uint32_t* status, void* stream);
+/*
+ * One call per torch.nn.Linear pass of the training step (the launches of the four entry points above, issued from C):
+ *   adk_linear_train_fwd: y[M][N] = x[M][K] . w[N][K]^T + bias; recs[4] <- {s_x, 1/s_x, s_w, 1/s_w} for the backward
+ *   adk_linear_train_bwd: dx[M][K] = g . w (if dx != NULL), dw[N][K] = g^T . x (if dw != NULL); rec_g[2] is scratch
+ * ws: adk_linear_train_ws_bytes(M, K, N) bytes of device scratch (operand planes), scratch: the 2 zeroed uint32 of
+ * adk_amax_scale.  K % 64 == 0, N % 64 == 0.
+ */
+int64_t adk_linear_train_ws_bytes(int M, int K, int N);
+int adk_linear_train_fwd(const float* x, const float* w, const float* bias, int M, int K, int N, float target,
+                         float* recs, void* ws, uint32_t* scratch, uint32_t* status, float* y, void* stream);
+int adk_linear_train_bwd(const float* g, const float* x, const float* w, int M, int K, int N, float target,
+                         const float* recs, float* rec_g, void* ws, uint32_t* scratch, uint32_t* status,
+                         float* dx, float* dw, void* stream);
 /* Tuning knob: run wide GEMMs as cta_group::2 CTA pairs (one MMA over M = 256 rows, each CTA staging half of the
  * weight tile).  On by default (5 % faster at two k-blocks per promotion, bit-identical results; see csrc/linear_tc.cu);
  * ADK_TC_PAIR=0 in the environment also turns it off. */

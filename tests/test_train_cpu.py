@@ -167,3 +167,14 @@ def test_two_rank_gradient_average(tmp_path):
     per_rank = [[torch.randn(3, 5, generator=g), torch.randn(7, generator=g), torch.randn(2, 2, 2, generator=g)] for g in gens]
     for i in range(3):
         assert torch.allclose(got[i], (per_rank[0][i] + per_rank[1][i]) / 2)
+
+
+def test_operand_space_formula_covers_the_library():
+    """`_TcWorkspace.operand_space` sizes the scratch in Python; it must never be below what the C side carves."""
+    from adsorbdiff_b200 import _cabi
+
+    lib = _cabi.load()
+    for M, K, N in [(1, 64, 64), (77, 1024, 512), (3700, 512, 1536), (11111, 512, 1024), (128, 256, 256), (129, 2048, 2048)]:
+        mp, np_, kr = T._pad(M, 128), T._pad(N, 128), T._pad(M, 64)
+        need = 4 * max(mp * K + N * K, mp * N + K * N + np_ * kr + K * kr) + 2048
+        assert need >= lib.adk_linear_train_ws_bytes(M, K, N)
