@@ -530,7 +530,9 @@ def run_ours(args):
 
     # ---- reference baselines (rank 0) ----------------------------------------------------------------------
     cores = os.cpu_count() or 1
-    cpu_val, cpu_dt, cpu_kind = cpu_rate(4, 2, 1, cores)
+    # bounded sample of the same workload: 16 systems x 5 steps is 10-12 s of the reference on 16 cores (--quick: 1 s)
+    cpu_sys, cpu_steps = (4, 2) if args.quick else (16, 5)
+    cpu_val, cpu_dt, cpu_kind = cpu_rate(cpu_sys, cpu_steps, 1, cores)
     reference_gpu = None
     if world == 1 and not args.quick:
         from oracle import ref_import
@@ -576,7 +578,8 @@ def run_ours(args):
         "roofline": roofline,
         "kernels": kernels,
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": cpu_kind,
-                         "sample": f"4 systems x 2 steps (+1 warm-up) of the same workload in {cpu_dt:.1f} s, fp32"},
+                         "sample": f"{cpu_sys} systems x {cpu_steps} steps (+1 warm-up) of the same workload in {cpu_dt:.1f} s, "
+                                   f"fp32, {cores} threads"},
     }
     if weak is not None:
         out["weak"] = weak
