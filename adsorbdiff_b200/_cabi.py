@@ -53,6 +53,8 @@ SIGNATURES = {
     "adk_linear_train_ws_bytes": (c_int64, [c_int, c_int, c_int]),
     "adk_linear_train_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P]),
     "adk_linear_train_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "adk_update_prep_bwd": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P]),
+    "adk_update_gate_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "adk_message": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int,
                             _P, _P, _P]),
     "adk_split_f16_transpose": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P]),
@@ -90,7 +92,7 @@ launch_count = 0  # kernels launched through this binding (bench.py reports it)
 
 _LAUNCHES = {  # kernels behind one entry-point call
     "adk_neighbors": 1, "adk_export_edges": 2, "adk_embed": 1, "adk_layernorm": 1, "adk_linear": 1, "adk_split_f16": 1, "adk_split_f16_multi": 1, "adk_linear_tc": 1,
-    "adk_message": 1, "adk_message_mma": 1, "adk_message_t5": 1, "adk_message_bwd": 4, "adk_amax_scale": 1, "adk_split_f16_dev": 1, "adk_split_f16_t_dev": 1, "adk_linear_tc_dev": 1, "adk_linear_train_fwd": 5, "adk_linear_train_bwd": 8, "adk_message_bwd_plan": 1, "adk_split_f16_transpose": 1, "adk_update_prep": 1, "adk_update_gate": 1, "adk_head_prep": 1, "adk_head_gate": 1, "adk_gather_rows": 1, "adk_scatter_rows": 1, "adk_mark_sources": 2,
+    "adk_message": 1, "adk_message_mma": 1, "adk_message_t5": 1, "adk_message_bwd": 4, "adk_amax_scale": 1, "adk_split_f16_dev": 1, "adk_split_f16_t_dev": 1, "adk_linear_tc_dev": 1, "adk_linear_train_fwd": 5, "adk_update_prep_bwd": 1, "adk_update_gate_bwd": 1, "adk_linear_train_bwd": 8, "adk_message_bwd_plan": 1, "adk_split_f16_transpose": 1, "adk_update_prep": 1, "adk_update_gate": 1, "adk_head_prep": 1, "adk_head_gate": 1, "adk_gather_rows": 1, "adk_scatter_rows": 1, "adk_mark_sources": 2,
     "adk_init_placement": 1, "adk_se3_step": 2, "adk_early_stop": 2,
 }
 

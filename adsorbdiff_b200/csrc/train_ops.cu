@@ -137,6 +137,111 @@ extern "C" int adk_split_f16_t_dev(const float* src, int64_t ld, int M, int C, c
     return 0;
 }
 
+// ---- backward of the update block's element-wise halves (forward: adk_update_prep / adk_update_gate, csrc/node_ops.cu;
+// reference: PaiNNUpdate.forward painn_denoising.py:601-623 under torch autograd) ------------------------------------
+namespace {
+
+// dot = sum_c v1 v2 / sqrt(F), cat = [x | sqrt(sum_c v2^2 + 1e-8)]  =>
+//   g_x = g_cat[:, :F];  g_v1[c] = g_dot v2[c] / sqrt(F);  g_v2[c] = g_dot v1[c] / sqrt(F) + g_cat[:, F:] v2[c] / norm
+__global__ void update_prep_bwd_kernel(const float* __restrict__ vp, const float* __restrict__ g_dot,
+                                       const float* __restrict__ g_cat, int N, int F, float inv_sqrt_h,
+                                       float* __restrict__ g_x, float* __restrict__ g_vp) {
+    const int F4 = F >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)N * F4) return;
+    const int n = (int)(idx / F4), f = ((int)(idx - (int64_t)n * F4)) << 2;
+    const float* r = vp + (int64_t)n * 3 * 2 * F + f;
+    float4 v1[3], v2[3];
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        v1[c] = *reinterpret_cast<const float4*>(r + c * 2 * F);
+        v2[c] = *reinterpret_cast<const float4*>(r + c * 2 * F + F);
+        q.x += v2[c].x * v2[c].x; q.y += v2[c].y * v2[c].y; q.z += v2[c].z * v2[c].z; q.w += v2[c].w * v2[c].w;
+    }
+    const float4 gd = *reinterpret_cast<const float4*>(g_dot + (int64_t)n * F + f);
+    const float4 gc0 = *reinterpret_cast<const float4*>(g_cat + (int64_t)n * 2 * F + f);
+    const float4 gc1 = *reinterpret_cast<const float4*>(g_cat + (int64_t)n * 2 * F + F + f);
+    *reinterpret_cast<float4*>(g_x + (int64_t)n * F + f) = gc0;
+    const float4 gs = make_float4(gd.x * inv_sqrt_h, gd.y * inv_sqrt_h, gd.z * inv_sqrt_h, gd.w * inv_sqrt_h);
+    const float4 gn = make_float4(gc1.x / sqrtf(q.x + 1e-8f), gc1.y / sqrtf(q.y + 1e-8f), gc1.z / sqrtf(q.z + 1e-8f),
+                                  gc1.w / sqrtf(q.w + 1e-8f));
+    float* o = g_vp + (int64_t)n * 3 * 2 * F + f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        *reinterpret_cast<float4*>(o + c * 2 * F) = make_float4(gs.x * v2[c].x, gs.y * v2[c].y, gs.z * v2[c].z, gs.w * v2[c].w);
+        *reinterpret_cast<float4*>(o + c * 2 * F + F) =
+            make_float4(gs.x * v1[c].x + gn.x * v2[c].x, gs.y * v1[c].y + gn.y * v2[c].y, gs.z * v1[c].z + gn.z * v2[c].z,
+                        gs.w * v1[c].w + gn.w * v2[c].w);
+    }
+}
+
+// x' = (x + (a + b dot) / sqrt(2)) s, vec' = vec + c v1  (s == 0: no multiply)  =>
+//   g_x = g_x' s;  g_a = g_x' s / sqrt(2);  g_b = g_a dot;  g_dot = g_a b;  g_c = sum_xyz g_vec' v1;  g_vec = g_vec';
+//   g_v1[xyz] = c g_vec'[xyz], g_v2 = 0  (written as this op's own g_vp; autograd adds the prep half's)
+__global__ void update_gate_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dot,
+                                       const float* __restrict__ vp, const float* __restrict__ scale,
+                                       const float* __restrict__ g_xo, const float* __restrict__ g_vo, int N, int F,
+                                       float* __restrict__ g_x, float* __restrict__ g_h, float* __restrict__ g_dot,
+                                       float* __restrict__ g_vp) {
+    const int F4 = F >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)N * F4) return;
+    const int n = (int)(idx / F4), f = ((int)(idx - (int64_t)n * F4)) << 2;
+    const float sc = *scale;
+    const float s = sc != 0.f ? sc : 1.0f;
+    const float is2 = 0.70710678118654752440f;
+    const float* hr = h + (int64_t)n * 3 * F + f;
+    const float4 bq = *reinterpret_cast<const float4*>(hr + F), cg = *reinterpret_cast<const float4*>(hr + 2 * F);
+    const int64_t xo = (int64_t)n * F + f;
+    const float4 dt = *reinterpret_cast<const float4*>(dot + xo);
+    const float4 gx = *reinterpret_cast<const float4*>(g_xo + xo);
+    const float4 gxs = make_float4(gx.x * s, gx.y * s, gx.z * s, gx.w * s);
+    const float4 ga = make_float4(gxs.x * is2, gxs.y * is2, gxs.z * is2, gxs.w * is2);
+    *reinterpret_cast<float4*>(g_x + xo) = gxs;
+    *reinterpret_cast<float4*>(g_dot + xo) = make_float4(ga.x * bq.x, ga.y * bq.y, ga.z * bq.z, ga.w * bq.w);
+    float4 gc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* r = vp + (int64_t)n * 3 * 2 * F + f;
+    float* o = g_vp + (int64_t)n * 3 * 2 * F + f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float4 v1 = *reinterpret_cast<const float4*>(r + c * 2 * F);
+        const float4 gv = *reinterpret_cast<const float4*>(g_vo + ((int64_t)n * 3 + c) * F + f);
+        gc.x += gv.x * v1.x; gc.y += gv.y * v1.y; gc.z += gv.z * v1.z; gc.w += gv.w * v1.w;
+        *reinterpret_cast<float4*>(o + c * 2 * F) = make_float4(cg.x * gv.x, cg.y * gv.y, cg.z * gv.z, cg.w * gv.w);
+        *reinterpret_cast<float4*>(o + c * 2 * F + F) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float* go = g_h + (int64_t)n * 3 * F + f;
+    *reinterpret_cast<float4*>(go) = ga;
+    *reinterpret_cast<float4*>(go + F) = make_float4(ga.x * dt.x, ga.y * dt.y, ga.z * dt.z, ga.w * dt.w);
+    *reinterpret_cast<float4*>(go + 2 * F) = gc;
+}
+
+}  // namespace
+
+extern "C" int adk_update_prep_bwd(const float* vp, const float* g_dot, const float* g_cat, int N, int F, float* g_x,
+                                   float* g_vp, void* stream) {
+    if (!vp || !g_dot || !g_cat || !g_x || !g_vp || N <= 0 || F <= 0 || (F & 3)) return ADK_EINVAL;
+    const int64_t n = (int64_t)N * (F >> 2);
+    update_prep_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, adk::as_stream(stream)>>>(
+        vp, g_dot, g_cat, N, F, 1.0f / sqrtf((float)F), g_x, g_vp);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int adk_update_gate_bwd(const float* h, const float* dot, const float* vp, const float* scale,
+                                   const float* g_x_out, const float* g_vec_out, int N, int F, float* g_x, float* g_h,
+                                   float* g_dot, float* g_vp, void* stream) {
+    if (!h || !dot || !vp || !scale || !g_x_out || !g_vec_out || !g_x || !g_h || !g_dot || !g_vp || N <= 0 || F <= 0 ||
+        (F & 3))
+        return ADK_EINVAL;
+    const int64_t n = (int64_t)N * (F >> 2);
+    update_gate_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, adk::as_stream(stream)>>>(
+        h, dot, vp, scale, g_x_out, g_vec_out, N, F, g_x, g_h, g_dot, g_vp);
+    ADK_LAUNCH_CHECK();
+    return 0;
+}
+
 // ---- one call per nn.Linear pass (host-side fusion: the launches below are what `TcLinearFn` used to issue one ctypes
 // call at a time; at ~40 Linear layers per step that was 7 ms of Python per training step) ------------------------
 namespace {

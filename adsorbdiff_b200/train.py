@@ -199,6 +199,55 @@ def _lin(net, lin, x):
     return y.reshape(*lead, y.shape[-1])
 
 
+class UpdatePrepFn(torch.autograd.Function):
+    """(x, vp) -> (dot, cat): vec_dot and [x | |v2|] of PaiNNUpdate.forward (painn_denoising.py:602-613), one kernel
+    each way instead of nine / fifteen eager ops."""
+
+    @staticmethod
+    def forward(ctx, x, vp):
+        x, vp = x.detach().contiguous(), vp.detach().contiguous()
+        N, F_ = x.shape
+        dot = torch.empty(N, F_, dtype=torch.float32, device=x.device)
+        cat = torch.empty(N, 2 * F_, dtype=torch.float32, device=x.device)
+        call("adk_update_prep", x.device, ptr(x), ptr(vp), N, F_, ptr(dot), ptr(cat), None, 0, 1.0, None)
+        ctx.save_for_backward(vp)
+        return dot, cat
+
+    @staticmethod
+    def backward(ctx, g_dot, g_cat):
+        (vp,) = ctx.saved_tensors
+        N, F_ = g_dot.shape
+        g_x = torch.empty(N, F_, dtype=torch.float32, device=vp.device)
+        g_vp = torch.empty_like(vp)
+        call("adk_update_prep_bwd", vp.device, ptr(vp), ptr(g_dot.contiguous()), ptr(g_cat.contiguous()), N, F_, ptr(g_x), ptr(g_vp))
+        return g_x, g_vp
+
+
+class UpdateGateFn(torch.autograd.Function):
+    """(x, vec, vp, h, dot) -> (x', vec'): the residual / gating half of PaiNNUpdate.forward (:614-623) plus the
+    fitted ScaleFactor (scale_factor.py:157-172)."""
+
+    @staticmethod
+    def forward(ctx, x, vec, vp, h, dot, scale):
+        vp, h, dot = vp.detach().contiguous(), h.detach().contiguous(), dot.detach().contiguous()
+        N, F_ = x.shape
+        x_out, vec_out = x.detach().clone(), vec.detach().clone()
+        call("adk_update_gate", x.device, ptr(h), ptr(dot), ptr(vp), ptr(scale), N, F_, ptr(x_out), ptr(vec_out), None, 0, 1.0, None)
+        ctx.save_for_backward(vp, h, dot, scale)
+        return x_out, vec_out
+
+    @staticmethod
+    def backward(ctx, g_xo, g_vo):
+        vp, h, dot, scale = ctx.saved_tensors
+        N, F_ = dot.shape
+        f32 = dict(dtype=torch.float32, device=vp.device)
+        g_x, g_h, g_dot, g_vp = torch.empty(N, F_, **f32), torch.empty(N, 3 * F_, **f32), torch.empty(N, F_, **f32), torch.empty_like(vp)
+        g_vo = g_vo.contiguous()
+        call("adk_update_gate_bwd", vp.device, ptr(h), ptr(dot), ptr(vp), ptr(scale), ptr(g_xo.contiguous()), ptr(g_vo), N, F_,
+             ptr(g_x), ptr(g_h), ptr(g_dot), ptr(g_vp))
+        return g_x, g_vo, g_vp, g_h, g_dot, None
+
+
 def _ssilu(x):
     """ScaledSiLU (gemnet_oc/layers/base_layers.py:65-72)"""
     return F.silu(x) * (1.0 / 0.6)
@@ -263,14 +312,20 @@ def forward_train(net, data, check: bool = True):
         m, u = net.message_layers[l], net.update_layers[l]
         xh = _mlp(net, m.x_proj, m.x_layernorm(x))
         x, vec = MessageFn.apply(x, vec, xh, m.rbf_proj.weight, m.rbf_proj.bias, net, p)
-        v1, v2 = torch.split(_lin(net, u.vec_proj, vec), F_, dim=-1)
-        vec_dot = (v1 * v2).sum(dim=1) * (1.0 / math.sqrt(F_))
-        h = _mlp(net, u.xvec_proj, torch.cat([x, torch.sqrt(torch.sum(v2 ** 2, dim=-2) + 1e-8)], dim=-1))
-        a, bq, c = torch.split(h, F_, dim=-1)
-        x = x + (a + bq * vec_dot) * INV_SQRT_2
-        vec = vec + c.unsqueeze(1) * v1
         sc = getattr(net, "upd_out_scalar_scale_%d" % l).scale_factor
-        x = torch.where(sc != 0.0, x * sc, x)   # ScaleFactor.forward multiplies only when fitted (no host sync here)
+        vp = _lin(net, u.vec_proj, vec)
+        if getattr(net, "train_fused_update", True):
+            vec_dot, cat = UpdatePrepFn.apply(x, vp)
+            h = _mlp(net, u.xvec_proj, cat)
+            x, vec = UpdateGateFn.apply(x, vec, vp, h, vec_dot, sc)
+        else:   # the same block in eager torch ops (kept for the parity test of the fused kernels)
+            v1, v2 = torch.split(vp, F_, dim=-1)
+            vec_dot = (v1 * v2).sum(dim=1) * (1.0 / math.sqrt(F_))
+            h = _mlp(net, u.xvec_proj, torch.cat([x, torch.sqrt(torch.sum(v2 ** 2, dim=-2) + 1e-8)], dim=-1))
+            a, bq, c = torch.split(h, F_, dim=-1)
+            x = x + (a + bq * vec_dot) * INV_SQRT_2
+            vec = vec + c.unsqueeze(1) * v1
+            x = torch.where(sc != 0.0, x * sc, x)   # ScaleFactor.forward multiplies only when fitted (no host sync)
     outs = []
     for head in ([net.out_forces, net.out_forces2] if net.so3_denoising else [net.out_forces]):
         hx, hv = _gated_block(net, head.output_network[0], x, vec, F_ // 2)
@@ -494,6 +549,7 @@ class TrainStep:
         self.pos_params = optim.get("denoising_pos_params", {})
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.step_count = 0
+        self.status_every = int(optim.get("status_every", 50))   # host read of the GEMMs' overflow word (one sync)
 
     def __call__(self, batch, noised: bool = False) -> torch.Tensor:
         net = self.net
@@ -516,4 +572,28 @@ class TrainStep:
         if self.shadow is not None:   # ExponentialMovingAverage.update (exponential_moving_average.py:71-97)
             torch._foreach_lerp_(self.shadow, [q.detach() for q in self.params], 1.0 - float(self.ema_decay))
         self.step_count += 1
+        if self.status_every and self.step_count % self.status_every == 0:
+            self.check_gemm_status()
         return loss.detach()
+
+    def check_gemm_status(self) -> None:
+        """The tensor-core GEMMs pick their prescales from the operands' own maxima, so the fp16 range can only be
+        left by an operand that already holds inf / nan; the status word says so (read every `status_every` steps)."""
+        ws = _TcWorkspace.get(self.params[0].device)
+        st = int(ws.status.item())
+        if st:
+            ws.status.zero_()
+            raise _cabi.AdkOverflow("a GEMM operand of the training step was not finite (fp16x2 split overflow bit set): "
+                                    "loss or gradients have diverged")
+
+    def params_in_sync(self) -> bool:
+        """Data parallel sanity: every rank holds bit-identical parameters (they start equal and see the same averaged
+        gradients).  One all-reduce of a checksum pair; call it outside timed regions."""
+        if self.world == 1:
+            return True
+        flat = torch.cat([q.detach().reshape(-1) for q in self.params]).double()
+        probe = torch.stack([flat.sum(), (flat * torch.arange(1, flat.numel() + 1, device=flat.device, dtype=torch.float64)).sum()])
+        lo, hi = probe.clone(), probe.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        return bool(torch.equal(lo, hi))

@@ -698,6 +698,8 @@ def run_train(args):
     clocks = sampler.stop() if sampler else None
     launches = (_cabi.launch_count - launches0) // args.steps
     mem = torch.cuda.max_memory_allocated(dev) / 2**30
+    in_sync = step.params_in_sync()      # every rank holds bit-identical parameters after the run
+    step.check_gemm_status()
     ref = None
     if rank == 0 and not args.quick:
         try:
@@ -719,6 +721,7 @@ def run_train(args):
             "e2e": {"value": world * B * args.steps / (ms / 1e3), "unit": "systems/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "peak_mem_gib": mem, "loss_first_last": [losses[0], losses[-1]],
+            "params_in_sync": in_sync,
             "reference_gpu": ref, "clocks": clocks,
         }))
     if world > 1:

@@ -165,6 +165,18 @@ int adk_linear_train_fwd(const float* x, const float* w, const float* bias, int 
 int adk_linear_train_bwd(const float* g, const float* x, const float* w, int M, int K, int N, float target,
                          const float* recs, float* rec_g, void* ws, uint32_t* scratch, uint32_t* status,
                          float* dx, float* dw, void* stream);
+/*
+ * Backward of adk_update_prep / adk_update_gate for the training step (reference: torch autograd through
+ * PaiNNUpdate.forward, painn_denoising.py:601-623).
+ *   adk_update_prep_bwd: from g_dot[N][F], g_cat[N][2F] -> g_x[N][F] (= g_cat[:, :F]) and g_vp[N][3][2F]
+ *   adk_update_gate_bwd: from g_x_out[N][F], g_vec_out[N][3][F] -> g_x[N][F], g_h[N][3F], g_dot[N][F] and
+ *                        g_vp[N][3][2F] (v1 half = c * g_vec_out, v2 half = 0); g_vec is g_vec_out itself
+ */
+int adk_update_prep_bwd(const float* vp, const float* g_dot, const float* g_cat, int N, int F, float* g_x, float* g_vp,
+                        void* stream);
+int adk_update_gate_bwd(const float* h, const float* dot, const float* vp, const float* scale, const float* g_x_out,
+                        const float* g_vec_out, int N, int F, float* g_x, float* g_h, float* g_dot, float* g_vp,
+                        void* stream);
 /* Tuning knob: run wide GEMMs as cta_group::2 CTA pairs (one MMA over M = 256 rows, each CTA staging half of the
  * weight tile).  On by default (5 % faster at two k-blocks per promotion, bit-identical results; see csrc/linear_tc.cu);
  * ADK_TC_PAIR=0 in the environment also turns it off. */

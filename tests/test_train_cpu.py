@@ -178,3 +178,27 @@ def test_operand_space_formula_covers_the_library():
         mp, np_, kr = T._pad(M, 128), T._pad(N, 128), T._pad(M, 64)
         need = 4 * max(mp * K + N * K, mp * N + K * N + np_ * kr + K * kr) + 2048
         assert need >= lib.adk_linear_train_ws_bytes(M, K, N)
+
+
+def _sync_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Fake:   # the two attributes params_in_sync reads
+        world = 2
+        params = [torch.nn.Parameter(torch.arange(6.0).reshape(2, 3)), torch.nn.Parameter(torch.ones(4))]
+
+    same = T.TrainStep.params_in_sync(Fake())
+    Fake.params[1].data[2] += 1e-6 * rank          # rank 1 drifts by one element
+    differ = T.TrainStep.params_in_sync(Fake())
+    if rank == 0:
+        torch.save((same, differ), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_params_in_sync_detects_a_drifting_rank(tmp_path):
+    out = str(tmp_path / "s.pt")
+    mp.spawn(_sync_worker, args=(2, 29743, out), nprocs=2, join=True)
+    same, differ = torch.load(out)
+    assert same is True and differ is False
