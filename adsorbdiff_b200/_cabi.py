@@ -14,7 +14,7 @@ import torch
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libadsorbdiff_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 SCHED_COLS = 6
 STATUS_EMPTY_SYSTEM = 1
 STATUS_ROW_OVERFLOW = 2
@@ -55,7 +55,7 @@ SIGNATURES = {
     "adk_linear_train_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
     "adk_update_prep_bwd": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P]),
     "adk_update_gate_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
-    "adk_message": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int,
+    "adk_message": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_int,
                             _P, _P, _P]),
     "adk_split_f16_transpose": (c_int, [_P, c_int, c_int, c_float, _P, _P, _P]),
     "adk_message_mma": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_int, c_int,

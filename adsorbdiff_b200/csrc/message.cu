@@ -47,6 +47,7 @@ struct MsParams {
     float* x_io;
     float* vec_out;
     // backward w.r.t. the node features (BWD instantiation, see csrc/message_bwd.cu)
+    const int32_t* row_sel;   // optional [N]: only rows with row_sel == 1 are computed, the others are left untouched
     const float* g_x;   // [N][F]    dL/d dx
     const float* g_v;   // [N][3][F] dL/d dvec
     float* d_xh;        // [N][3F]
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(MS_THREADS, 2) message_kernel(MsParams P) {
 
     const int row_end = min(P.N, (int)(blockIdx.x + 1) * ROWS_PER_CTA);
     for (int t = blockIdx.x * ROWS_PER_CTA + warp; t < row_end; t += MS_WARPS) {
+        if (P.row_sel && P.row_sel[t] != 1) continue;
         const int start = P.row_start[t], deg = P.row_deg[t];
         float2 dx = make_float2(0.f, 0.f);
         float2 dv[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -285,7 +287,7 @@ void fill_params(MsParams& P, const int32_t* row_start, const int32_t* row_deg, 
     P.env_a = (float)(-(p + 1) * (p + 2) / 2);
     P.env_b = (float)(p * (p + 2));
     P.env_c = (float)(-p * (p + 1) / 2);
-    P.x_io = nullptr; P.vec_out = nullptr; P.g_x = nullptr; P.g_v = nullptr; P.d_xh = nullptr; P.d_vec = nullptr;
+    P.x_io = nullptr; P.vec_out = nullptr; P.row_sel = nullptr; P.g_x = nullptr; P.g_v = nullptr; P.d_xh = nullptr; P.d_vec = nullptr;
 }
 
 size_t smem_bytes(int R) {
@@ -309,7 +311,7 @@ int adk_message_bwd_nodes(const int32_t* row_start, const int32_t* row_deg, cons
     return 0;
 }
 
-extern "C" int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
+extern "C" int adk_message(const int32_t* row_sel, const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
                            const float* e_geo, const float* xh, const float* vec_in, const float* w_rbf,
                            const float* b_rbf, const float* rbf_offset, int N, int F, int R, float cutoff,
                            int envelope_exponent, float* x_io, float* vec_out, void* stream) {
@@ -319,7 +321,7 @@ extern "C" int adk_message(const int32_t* row_start, const int32_t* row_deg, con
     if (F % FS != 0 || R < NTAPS || (R & 3) || envelope_exponent < 1 || vec_in == vec_out) return ADK_EINVAL;
     MsParams P;
     fill_params(P, row_start, row_deg, e_src, e_geo, xh, vec_in, w_rbf, b_rbf, rbf_offset, N, F, R, cutoff, envelope_exponent);
-    P.x_io = x_io; P.vec_out = vec_out;
+    P.x_io = x_io; P.vec_out = vec_out; P.row_sel = row_sel;
     const size_t smem = smem_bytes(R);
     dim3 grid((N + ROWS_PER_CTA - 1) / ROWS_PER_CTA, F / FS);
     message_kernel<false><<<grid, MS_THREADS, smem, adk::as_stream(stream)>>>(P);

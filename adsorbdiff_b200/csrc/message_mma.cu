@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) message_mma_kernel(MmParams P) 
     const int b_first = blockIdx.x * P.sys_per_cta, b_end = min(P.B, b_first + P.sys_per_cta);
     for (int b = b_first; b < b_end; ++b) {
     const int a0 = P.atom_off[b], n = P.atom_off[b + 1] - a0;
+    if (n > P.n_max) continue;   // larger than the staging area this launch was sized for: another kernel owns it (row_sel == 0 there)
     // ---- stage the system's source features: one 128-byte segment per (atom, group) per warp ----
     {
         // feature f = nt * 8 + 2 * qt + h of the slice lands at [g][qt][nt][h]

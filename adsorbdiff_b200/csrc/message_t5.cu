@@ -289,6 +289,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
     const int a0 = P.atom_off[b], n = P.atom_off[b + 1] - a0;
     const int F = P.F, R = P.R;
     const bool has_vec = P.vec_in != nullptr;
+    if (n > P.n_max) return;   // larger than the staging area this launch was sized for: another kernel owns it (row_sel == 0 there)
     T5_CTA_STAMP(0);
 
     // ---- one-time setup ----------------------------------------------------------------------------------

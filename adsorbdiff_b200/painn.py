@@ -371,15 +371,31 @@ class PaiNN(nn.Module):
         p.tab_xh = torch.empty(ne, 3 * F, **f32)
         p.tab_spx = torch.zeros(2 * p.tab_rows * F, **f16)
         p.tab_sph = torch.zeros(2 * p.tab_rows * F, **f16)
-        # does a system's staged slice fit the shared memory of the warp-MMA message kernel?  (else: adk_message)
-        p.mma_fits = (self.num_rbf % 16 == 0 and 16 <= self.num_rbf <= 128
-                      and _cabi.load().adk_message_mma_smem_bytes(self.num_rbf, p.n_max) > 0)
-        # tcgen05 message kernel: 8 slice-CTAs per system; below ~2 CTAs per SM the row-split mma kernel wins
-        # (the kernel evaluates the Gaussian centres arithmetically as k / (R - 1): check the buffer really is that)
+        # Message kernels by system size: the tcgen05 kernel stages a whole system's sources in shared memory (up to ~110
+        # atoms), the warp-MMA kernel up to ~190, the row-tiled SIMT kernel anything.  A batch is split between them
+        # system by system (`p.engines`: [(name, n_cap, per-atom 0/1 mask or None)]); one oversized system does not take
+        # the rest of the batch off the fast path.  (t5 evaluates the Gaussian centres arithmetically as k / (R - 1):
+        # the buffer must really be that.)
+        lib = _cabi.load()
         off = self.radial_basis.rbf.offset
         uniform = bool(torch.equal(off.detach().cpu(), torch.linspace(0.0, 1.0, self.num_rbf)))
-        p.t5_fits = (self.num_rbf == 128 and F % 64 == 0 and p.B * (F // 64) >= self.t5_min_ctas and uniform
-                     and _cabi.load().adk_message_t5_smem_bytes(self.num_rbf, p.n_max) > 0)
+        t5_ok = self.num_rbf == 128 and F % 64 == 0 and p.B * (F // 64) >= self.t5_min_ctas and uniform
+        mma_ok = self.num_rbf % 16 == 0 and 16 <= self.num_rbf <= 128
+
+        def cap(fn, ok):   # largest system the kernel takes
+            if not ok:
+                return 0
+            lo, hi = 0, min(p.n_max, _cabi.MAX_ATOMS_PER_SYSTEM)
+            if fn(self.num_rbf, hi) > 0:
+                return hi
+            while lo < hi:   # the smem need grows with n: bisect
+                mid = (lo + hi + 1) // 2
+                lo, hi = (mid, hi) if fn(self.num_rbf, mid) > 0 else (lo, mid - 1)
+            return lo
+
+        p.t5_cap, p.mma_cap = cap(lib.adk_message_t5_smem_bytes, t5_ok), cap(lib.adk_message_mma_smem_bytes, mma_ok)
+        p.t5_fits, p.mma_fits = p.t5_cap >= p.n_max, p.mma_cap >= p.n_max
+        p.engine_cache = {}
         self._plan_cache = p
         return p
 
@@ -628,40 +644,48 @@ class PaiNN(nn.Module):
                 call("adk_mark_sources", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(out_rows[0]),
                      int(out_rows[0].numel()), N, ptr(p.sel2))
                 row_sel = p.sel2
-            if self.msg == "t5" and p.t5_fits:
-                planes = self._tc_ok(u.vec_proj) and not pruned
-                call("adk_message_t5", dev, ptr(p.atom_off), p.B, p.n_max, ptr(row_sel) if row_sel is not None else None,
-                     ptr(p.row_start), ptr(p.row_deg),
-                     ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None,
-                     ptr(self._wsplit(p, m.rbf_proj)), self._sw(m.rbf_proj), ptr(m.rbf_proj.bias),
-                     ptr(self.radial_basis.rbf.offset), F, R, float(self.cutoff), self.radial_basis.exponent,
-                     float(self.msg_t5_comp), ptr(p.x), ptr(vout), ptr(p.sp_v) if planes else None, p.rows_3n,
-                     self._sa(u.vec_proj, self.V_SCALE), ptr(p.status))
-                vec_presplit = planes
-                if pruned:
-                    self._finish_rows(p, out_rows[0], l, vout)
-                    return
-            elif self.msg in ("mma", "t5") and p.mma_fits:
-                wt = p.wt_rbf[l]
-                if not weights_ready:
-                    call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self._sw(m.rbf_proj), ptr(wt),
-                         ptr(p.status))
-                planes = self._tc_ok(u.vec_proj) and not pruned
-                call("adk_message_mma", dev, ptr(p.atom_off), p.B, p.n_max, ptr(row_sel) if row_sel is not None else None,
-                     ptr(p.row_start), ptr(p.row_deg),
-                     ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wt),
-                     self._sw(m.rbf_proj), ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R,
-                     float(self.cutoff), self.radial_basis.exponent, float(self.msg_comp), ptr(p.x), ptr(vout),
-                     ptr(p.sp_v) if planes else None, p.rows_3n, self._sa(u.vec_proj, self.V_SCALE), ptr(p.status))
-                vec_presplit = planes
-                if pruned:
-                    self._finish_rows(p, out_rows[0], l, vout)
-                    return
-            else:
-                call("adk_message", dev, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(p.xh),
-                     ptr(vin) if vin is not None else None, ptr(m.rbf_proj.weight), ptr(m.rbf_proj.bias),
-                     ptr(self.radial_basis.rbf.offset), N, F, R, float(self.cutoff), self.radial_basis.exponent,
-                     ptr(p.x), ptr(vout))
+            engines = self._message_engines(p)
+            any_simt = any(name == "simt" for name, _, _ in engines)
+            planes = self._tc_ok(u.vec_proj) and not pruned and not any_simt
+            for name, n_cap, mask in engines:
+                sel = row_sel
+                if mask is not None:
+                    # rows of the systems this kernel owns; the sampler's row selection applies inside them (the SIMT
+                    # kernel has no pass-through mode: it computes all rows of its systems, a superset)
+                    if row_sel is None or name == "simt":
+                        sel = mask
+                    else:
+                        sel = p.engine_cache[("buf", name)]
+                        torch.mul(row_sel, mask, out=sel)
+                if name == "t5":
+                    call("adk_message_t5", dev, ptr(p.atom_off), p.B, n_cap, ptr(sel) if sel is not None else None,
+                         ptr(p.row_start), ptr(p.row_deg),
+                         ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None,
+                         ptr(self._wsplit(p, m.rbf_proj)), self._sw(m.rbf_proj), ptr(m.rbf_proj.bias),
+                         ptr(self.radial_basis.rbf.offset), F, R, float(self.cutoff), self.radial_basis.exponent,
+                         float(self.msg_t5_comp), ptr(p.x), ptr(vout), ptr(p.sp_v) if planes else None, p.rows_3n,
+                         self._sa(u.vec_proj, self.V_SCALE), ptr(p.status))
+                elif name == "mma":
+                    wt = p.wt_rbf[l]
+                    if not weights_ready:
+                        call("adk_split_f16_transpose", dev, ptr(m.rbf_proj.weight), 3 * F, R, self._sw(m.rbf_proj), ptr(wt),
+                             ptr(p.status))
+                    call("adk_message_mma", dev, ptr(p.atom_off), p.B, n_cap, ptr(sel) if sel is not None else None,
+                         ptr(p.row_start), ptr(p.row_deg),
+                         ptr(p.e_src), ptr(p.e_geo), ptr(p.xh), ptr(vin) if vin is not None else None, ptr(wt),
+                         self._sw(m.rbf_proj), ptr(m.rbf_proj.bias), ptr(self.radial_basis.rbf.offset), F, R,
+                         float(self.cutoff), self.radial_basis.exponent, float(self.msg_comp), ptr(p.x), ptr(vout),
+                         ptr(p.sp_v) if planes else None, p.rows_3n, self._sa(u.vec_proj, self.V_SCALE), ptr(p.status))
+                else:
+                    call("adk_message", dev, ptr(sel) if sel is not None else None, ptr(p.row_start), ptr(p.row_deg),
+                         ptr(p.e_src), ptr(p.e_geo), ptr(p.xh),
+                         ptr(vin) if vin is not None else None, ptr(m.rbf_proj.weight), ptr(m.rbf_proj.bias),
+                         ptr(self.radial_basis.rbf.offset), N, F, R, float(self.cutoff), self.radial_basis.exponent,
+                         ptr(p.x), ptr(vout))
+            vec_presplit = planes
+            if pruned:
+                self._finish_rows(p, out_rows[0], l, vout)
+                return
             cur = 1 - cur
             vec = p.vec[cur]
             if trace is not None:
@@ -670,6 +694,36 @@ class PaiNN(nn.Module):
             if trace is not None:
                 trace[f"upd{l}.x"], trace[f"upd{l}.vec"] = p.x.clone(), vec.clone()
         self._heads(p, p.vec[cur], heads_presplit)
+
+    def _message_engines(self, p):
+        """[(kernel, n_cap, per-atom 0/1 mask or None)]: which message kernel owns which systems of this plan, under the
+        present `self.msg` ("t5": tcgen05 -> warp-MMA -> SIMT by system size; "mma": warp-MMA -> SIMT; "simt")."""
+        key = self.msg
+        hit = p.engine_cache.get(key)
+        if hit is not None:
+            return hit
+        chain = {"t5": [("t5", p.t5_cap), ("mma", p.mma_cap)], "mma": [("mma", p.mma_cap)]}.get(self.msg, [])
+        chain = chain + [("simt", 1 << 30)]
+        nat = p.natoms_cpu
+        out, lo = [], 0
+        batch_of_atom = None
+        for name, hi in chain:
+            if hi <= lo:
+                continue
+            sys_in = (nat > lo) & (nat <= hi)
+            lo = hi
+            if not bool(sys_in.any()):
+                continue
+            if bool(sys_in.all()):
+                out.append((name, p.n_max, None))
+                break
+            if batch_of_atom is None:
+                batch_of_atom = torch.repeat_interleave(torch.arange(p.B), nat)
+            mask = sys_in[batch_of_atom].to(torch.int32).to(p.device).contiguous()
+            p.engine_cache[("buf", name)] = torch.empty_like(mask)
+            out.append((name, int(nat[sys_in].max()), mask))
+        p.engine_cache[key] = out
+        return out
 
     def _update(self, p, l: int, vec: torch.Tensor, vec_presplit: bool) -> bool:
         """PaiNNUpdate + ScaleFactor of layer l on the rows of plan `p` (painn_denoising.py:601-623, 449-451).

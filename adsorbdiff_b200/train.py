@@ -48,7 +48,7 @@ class MessageFn(torch.autograd.Function):
         vec_in = vec.detach().contiguous() if vec is not None else None
         vec_out = torch.empty(N, 3, F_, dtype=torch.float32, device=x.device)
         xh_c, w_c, b_c = xh.detach().contiguous(), w.detach().contiguous(), b.detach().contiguous()
-        call("adk_message", p.device, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(xh_c),
+        call("adk_message", p.device, None, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(xh_c),
              ptr(vec_in), ptr(w_c), ptr(b_c), ptr(net.radial_basis.rbf.offset), N, F_, R, float(net.cutoff),
              net.radial_basis.exponent, ptr(x_out), ptr(vec_out))
         ctx.net, ctx.p, ctx.has_vec = net, p, vec is not None

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ADK_ABI_VERSION 2
+#define ADK_ABI_VERSION 3
 
 #define ADK_EINVAL (-22)   /* bad argument (null pointer, unsupported size) */
 #define ADK_ERANGE (-34)   /* size beyond a compiled capacity (images, atoms per system) */
@@ -203,8 +203,10 @@ int adk_linear_tc(const void* a_split, int64_t a_plane_rows, int M, const void* 
  *   x_io[N][F]: in = x, out = (x + dx)/sqrt(2);  vec_out[N][3][F] = vec_in + dvec
  *   (vec_out must not alias vec_in: other rows still read it).
  * Row-tiled SIMT kernel, no per-system staging: the path for systems too large for adk_message_mma.
+ *   row_sel: NULL, or [N]: only rows with row_sel == 1 are computed, every other row of x_io / vec_out is left
+ *   untouched (a mixed batch is split between the three message kernels by system size, see PaiNN.plan).
  */
-int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
+int adk_message(const int32_t* row_sel, const int32_t* row_start, const int32_t* row_deg, const int32_t* e_src,
                 const float* e_geo, const float* xh, const float* vec_in, const float* w_rbf,
                 const float* b_rbf, const float* rbf_offset, int N, int F, int R, float cutoff,
                 int envelope_exponent, float* x_io, float* vec_out, void* stream);
@@ -214,7 +216,8 @@ int adk_message(const int32_t* row_start, const int32_t* row_deg, const int32_t*
  * system's xh / vec slices and the fp16x2 planes of the w_rbf slice are staged in shared memory, and
  * rbfh of 16 distance-sorted edges at a time is a mma.sync m16n8k16 micro-GEMM over the union RBF window.
  *   wt_split = adk_split_f16_transpose(w_rbf[3F][R], scale = w_scale) -> fp16 [2][R][3F]
- *   n_max = largest system; returns ADK_ERANGE when a system's slices do not fit shared memory.
+ *   n_max = the system size the launch is sized for (ADK_ERANGE when its slices do not fit shared memory); systems
+ *   with more atoms are skipped (their rows belong to another message kernel, row_sel == 0 there).  Same for adk_message_t5.
  */
 int adk_split_f16_transpose(const float* w, int rows, int cols, float scale, void* dst, uint32_t* status,
                             void* stream);

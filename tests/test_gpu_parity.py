@@ -263,6 +263,41 @@ def test_large_system_falls_back_and_matches(weights):
         assert float((got.double().cpu() - ref).abs().max() / ref.abs().max()) < FEATURE_TOL
 
 
+def test_mixed_size_batch_is_split_between_the_message_kernels(weights, sampler_weights):
+    """One batch with an 82-, a 127- and a 218-atom system: the tcgen05 kernel (stages <= ~110 atoms), the warp-MMA
+    kernel (<= ~190) and the row-tiled kernel each take the systems they fit -- one oversized system must not push the
+    rest of the batch off the fast path.  Every system's rows are bit-identical to running that system alone (same
+    kernel, same summation order), outputs agree with the fp64 oracle, and the sampler's row-selected tail gives the
+    same positions as the full forward."""
+    _reset_sticky_pbc()
+    m = PaiNN(None, 0, 1, so3_denoising=True).to("cuda:0").eval()
+    m.load_state_dict(weights, strict=True)
+    parts = [S.make_system(3), S.make_system(41, size=(5, 5, 5)), S.make_system(31, size=(6, 6, 6))]
+    b = S.collate(parts)
+    nat = [int(v) for v in b.natoms]
+    assert nat[0] <= 111 < nat[1] <= 190 < nat[2]
+    f1, f2 = m(b.clone().to("cuda:0"))
+    engines = m._message_engines(m._plan_cache)
+    assert [e[0] for e in engines] == ["t5", "mma", "simt"] and all(e[2] is not None for e in engines)
+    o64 = O.painn_forward(weights, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms, dtype=torch.float64)
+    for got, ref in zip((f1, f2), o64):
+        assert float((got.double().cpu() - ref).abs().max() / ref.abs().max()) < FEATURE_TOL
+    off = np.cumsum([0] + nat)
+    for i, part in enumerate(parts):
+        a1, a2 = m(S.collate([part]).to("cuda:0"))
+        assert torch.equal(a1, f1[off[i]:off[i + 1]]) and torch.equal(a2, f2[off[i]:off[i + 1]])
+    # the sampler on the same batch: row-selected tail == full forward, three replayed steps
+    m.load_state_dict(sampler_weights, strict=True)
+    params = dict(num_steps=4, ads_std_low=0.1, ads_std_high=10, rot_std_low=0.01, rot_std_high=1.55, early_stop=False)
+    noise = torch.rand(3, 3, generator=torch.Generator().manual_seed(5))
+    finals = []
+    for full in (False, True):
+        d = b.clone().to("cuda:0")
+        Denoiser(d, m, dict(params, full_forward=full), device="cuda:0", init_noise=noise).run()
+        finals.append(d.pos.clone())
+    assert torch.equal(finals[0], finals[1])
+
+
 def test_early_stop_matches_reference_semantics(sampler_weights):
     """With a vanishing score the COM update is ~0, the reference counts 10 converged steps and breaks BEFORE
     applying the 10th update (denoising_torch.py:312-320)."""
