@@ -292,6 +292,11 @@ def forward_train(net, data, check: bool = True):
     forces [N,3] (and forces2 with `so3_denoising`) attached to the autograd graph of the parameters.  `check` raises
     on the device status word (empty system, bad element, row overflow) before returning; it waits only for the
     neighbour search, not for the forward.  `TrainStep` defers it until the backward pass has been enqueued."""
+    with torch.autocast(device_type="cuda", enabled=False):   # PaiNN trains in fp32 (no AMP for this model in the
+        return _forward_train_fp32(net, data, check)           # reference, run.py:21-25); the kernels take fp32 only
+
+
+def _forward_train_fp32(net, data, check: bool):
     p, z, pos = net._prepare(data)
     net._graph(p, pos)
     if torch.is_grad_enabled():
@@ -542,7 +547,8 @@ class TrainStep:
         name = optim.get("optimizer", "AdamW")
         if name != "AdamW":
             raise NotImplementedError("the denoising configs train with AdamW")
-        self.optimizer = torch.optim.AdamW(groups, lr=float(optim.get("lr_initial", 1e-4)), fused=dev.type == "cuda")
+        extra = {k: v for k, v in optim.get("optimizer_params", {}).items() if k != "weight_decay"}   # betas, eps, amsgrad ...
+        self.optimizer = torch.optim.AdamW(groups, lr=float(optim.get("lr_initial", 1e-4)), fused=dev.type == "cuda", **extra)
         self.clip = optim.get("clip_grad_norm")
         self.ema_decay = optim.get("ema_decay")
         self.shadow = [q.detach().clone() for q in self.params] if self.ema_decay else None

@@ -161,6 +161,17 @@ def test_message_backward_alone(net):
         assert err <= 2e-5, (name, err)
 
 
+def test_training_forward_ignores_autocast(net):
+    """Called under torch.autocast (a trainer started with --amp) the model still computes and returns fp32, bit-identical
+    to the call without it ("under autocast the drop-in must still return fp32")."""
+    b = CASES["tiny"][0]().to("cuda:0")
+    net.train()
+    f1, f2 = net(b)
+    with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+        a1, a2 = net(b)
+    assert a1.dtype == torch.float32 and torch.equal(a1, f1) and torch.equal(a2, f2)
+
+
 def test_message_backward_is_deterministic(net):
     b = CASES["jit2"][0]().to("cuda:0")
     G = torch.randn(b.pos.shape[0], 3, device="cuda")
