@@ -36,8 +36,7 @@ def _oracle_grads(weights, b, G1, G2, dtype=torch.float64):
     return P, o1.detach(), o2.detach()
 
 
-@pytest.mark.parametrize("gemm", ["tc", "torch"])
-@pytest.mark.parametrize("name", ["tiny", "jit2"])
+@pytest.mark.parametrize("name,gemm", [("tiny", "tc"), ("tiny", "torch"), ("jit2", "tc"), ("jit2", "torch"), ("mixed", "tc")])
 def test_backward_matches_oracle(name, gemm, net, weights):
     """`gemm`: the nn.Linear layers' three GEMMs on the tcgen05 kernel with device-side prescales ("tc", the default)
     or on cuBLAS fp32 through torch ("torch")."""
@@ -209,6 +208,17 @@ def test_train_step_reduces_loss_and_updates_ema(net):
     with torch.no_grad():
         f1, f2 = net(S.make_batch(2).to("cuda:0"))
     assert torch.isfinite(f1).all() and torch.isfinite(f2).all()
+
+
+def test_train_step_on_one_system_and_on_a_large_one(net):
+    """Degenerate batch shapes of the step: a single system (one row chunk per few rows, GEMMs on the narrow tiles) and a
+    218-atom slab (more rows than any sampler test, row degree up to 100)."""
+    tables = T.IGSO3Tables("cuda:0", n_eps=100, x_n=200, L=300)
+    step = T.TrainStep(net, dict(lr_initial=1e-6, denoising_pos_params=PARAMS, clip_grad_norm=100), tables)
+    for batch in (S.make_batch(1), S.collate([S.make_system(31, size=(6, 6, 6)), S.make_system(2)])):
+        losses = [float(step(batch.clone().to("cuda:0"))) for _ in range(2)]
+        assert np.isfinite(losses).all(), losses
+    step.check_gemm_status()
 
 
 def test_malformed_batch_raises_before_the_optimizer_step(net):
