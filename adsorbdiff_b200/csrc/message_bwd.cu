@@ -207,16 +207,36 @@ __global__ void __launch_bounds__(BWW_THREADS, 3) message_bwd_weights_kernel(BwP
             for (int g = 0; g < 3; ++g) db[g] += dr[g];
             __syncwarp();
             const float4* tp = reinterpret_cast<const float4*>(s_tap[warp][par]);
+            // the 16 live taps [o, o + 16) lie inside five consecutive 4-tap chunks starting at chunk o >> 2: a
+            // warp-uniform switch selects that chunk range with STATIC register indices (60 FMAs instead of 96)
+            switch (o >> 2) {
+#define ADK_BWW_CASE(C)                                                              \
+    case C:                                                                          \
+        _Pragma("unroll") for (int r4 = C; r4 < C + 5; ++r4) {                       \
+            const float4 t4 = tp[r4];                                                \
+            _Pragma("unroll") for (int g = 0; g < 3; ++g) {                          \
+                W[g][4 * r4 + 0] = fmaf(dr[g], t4.x, W[g][4 * r4 + 0]);              \
+                W[g][4 * r4 + 1] = fmaf(dr[g], t4.y, W[g][4 * r4 + 1]);              \
+                W[g][4 * r4 + 2] = fmaf(dr[g], t4.z, W[g][4 * r4 + 2]);              \
+                W[g][4 * r4 + 3] = fmaf(dr[g], t4.w, W[g][4 * r4 + 3]);              \
+            }                                                                        \
+        }                                                                            \
+        break;
+                ADK_BWW_CASE(0) ADK_BWW_CASE(1) ADK_BWW_CASE(2)
+                default: {   // o >> 2 == 3: chunks 3..7 (the window cannot start beyond tap 15)
 #pragma unroll
-            for (int r4 = 0; r4 < 8; ++r4) {
-                const float4 t4 = tp[r4];
+                    for (int r4 = 3; r4 < 8; ++r4) {
+                        const float4 t4 = tp[r4];
 #pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    W[g][4 * r4 + 0] = fmaf(dr[g], t4.x, W[g][4 * r4 + 0]);
-                    W[g][4 * r4 + 1] = fmaf(dr[g], t4.y, W[g][4 * r4 + 1]);
-                    W[g][4 * r4 + 2] = fmaf(dr[g], t4.z, W[g][4 * r4 + 2]);
-                    W[g][4 * r4 + 3] = fmaf(dr[g], t4.w, W[g][4 * r4 + 3]);
+                        for (int g = 0; g < 3; ++g) {
+                            W[g][4 * r4 + 0] = fmaf(dr[g], t4.x, W[g][4 * r4 + 0]);
+                            W[g][4 * r4 + 1] = fmaf(dr[g], t4.y, W[g][4 * r4 + 1]);
+                            W[g][4 * r4 + 2] = fmaf(dr[g], t4.z, W[g][4 * r4 + 2]);
+                            W[g][4 * r4 + 3] = fmaf(dr[g], t4.w, W[g][4 * r4 + 3]);
+                        }
+                    }
                 }
+#undef ADK_BWW_CASE
             }
             par ^= 1;   // the other buffer is free again after the __syncwarp of the NEXT item
             it0 = it1; it1 = it2; f0 = f1;
