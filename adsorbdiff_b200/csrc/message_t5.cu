@@ -670,13 +670,22 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                     tile_body<2, 2>(t_addr, meta_g, src_lane, scale2, bias2, s0, acc);
                 }
                 if (warp == T5_EPI_WARP0 + 2) T5_STAMP(ti, 10);
-                if (tile_last(tl)) {
-                    // the row group is complete: residuals, write-out, reset
+                // The accumulator and the tile's metadata have been consumed (row sums are in registers): hand the slot back
+                // BEFORE the write-out of a finished row group, whose global round trip (~2 300 cycles) used to keep
+                // the slot -- and with it the generator and the MMA of this team's next tile -- waiting.
+                const bool group_done = tile_last(tl);
+                int rr[4] = {-1, -1, -1, -1};
+                if (group_done) {
                     const int* rows = reinterpret_cast<const int*>(meta_g + T5_META_ROW);
                     const int nr = phase == 0 ? 4 : 2;
-                    int rr[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) rr[i] = i < nr ? rows[s0 + (i < nr ? i : 0)] : -1;
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d_empty(ds));
+                if (group_done) {
+                    // the row group is complete: residuals, write-out, reset
                     if (phase == 0 && !upper) {
                         float xin[4];
 #pragma unroll
@@ -718,9 +727,6 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
 #pragma unroll
                     for (int i = 0; i < 12; ++i) acc[i] = 0.f;
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(d_empty(ds));
                 if (warp == T5_EPI_WARP0 + 2) T5_STAMP(ti, 11);
             }
             __syncthreads();
