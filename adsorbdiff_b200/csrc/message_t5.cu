@@ -139,7 +139,8 @@ __device__ __forceinline__ bool tile_last(uint32_t t) { return (t >> 24) != 0u; 
 // `v` holds the accumulator columns of this thread's feature.  Padding columns point at a zero source row, so no
 // per-edge predicates are needed.  p[c] = (sum over even edges, sum over odd edges) of output component c.
 #ifndef T5_EXP
-#define T5_EXP 0   // bring-up experiments (scripts/build_exp_libs.sh): 1 = no TMEM loads, 2 = no source loads, 3 = empty epilogue
+#define T5_EXP 0   // ablation builds (scripts/build_exp_libs.sh): 1 = no TMEM loads, 2 = no source loads, 3 = empty epilogue,
+                   // 4 = no MMAs, 5 = empty epilogue + no generator arithmetic / operand stores, 6 = 5 + no MMAs
 #endif
 template <int MODE, int NE>   // MODE 0: dx (m1), 1: m3 * r_hat, 2: p2 * m2
 __device__ __forceinline__ void edge_block(const uint32_t* v, const uint8_t* meta, int col, const uint8_t* src_lane,
@@ -437,7 +438,8 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
     umma_f16(d_tmem, mk_desc(a_lo[s]), mk_desc(bl_lo + 2 * (s)), idesc, acc);                                      \
     umma_f16(d_tmem, mk_desc(a_lo[s] + (T5_W_PLANE >> 4)), mk_desc(bh_lo + 2 * (s)), idesc, 1u);
 #define T5_MMA_MAIN(s) umma_f16(d_tmem, mk_desc(a_lo[s]), mk_desc(bh_lo + 2 * (s)), idesc, 1u);
-                        if (nks == 4) {
+                        if (T5_EXP == 4 || T5_EXP == 6) {
+                        } else if (nks == 4) {
                             T5_MMA_CORR(0, acc0) T5_MMA_CORR(1, 1u) T5_MMA_CORR(2, 1u) T5_MMA_CORR(3, 1u)
                             T5_MMA_MAIN(0) T5_MMA_MAIN(1) T5_MMA_MAIN(2) T5_MMA_MAIN(3)
                         } else if (nks == 3) {
@@ -552,7 +554,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                 const float d0 = fmaf(-(float)k8, h0, s);   // s - mu_k8, one rounding
                 uint32_t hi[12], lo[12];
 #pragma unroll
-                for (int i = 0; i < 12; ++i) {
+                for (int i = 0; i < (T5_EXP >= 5 ? 0 : 12); ++i) {
                     const float t0 = fmaf(-(float)(2 * i), h0, d0) * P.coeff_sqrt;
                     const float t1 = fmaf(-(float)(2 * i + 1), h0, d0) * P.coeff_sqrt;
                     const float g0 = env * ex2_approx(-t0 * t0), g1 = env * ex2_approx(-t1 * t1);
@@ -590,7 +592,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
 #pragma unroll
                     for (int qq = 0; qq < 3; ++qq) {
                         const int ch = qq - q0;
-                        if (ch >= 0 && ch < 2 * nks) {
+                        if (T5_EXP < 5 && ch >= 0 && ch < 2 * nks) {
                             valued |= 1u << ch;
                             const uint32_t addr = bb + (uint32_t)((ch ^ (c & 7)) * 16);
                             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hi[4 * qq]), "r"(hi[4 * qq + 1]), "r"(hi[4 * qq + 2]), "r"(hi[4 * qq + 3]) : "memory");
@@ -662,7 +664,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                 if (warp == T5_EPI_WARP0 + 2) T5_STAMP(ti, 9);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ds * T5_TILE;
-                if (T5_EXP == 3) {
+                if (T5_EXP == 3 || T5_EXP >= 5) {
                 } else if (phase == 0) {
                     if (!upper) tile_body<0, 4>(t_addr, meta_g, src_lane, scale2, bias2, s0, acc);
                     else tile_body<1, 4>(t_addr, meta_g, src_lane, scale2, bias2, s0, acc);

@@ -1,5 +1,6 @@
 #!/bin/bash
-# bring-up experiment builds of the library: message_t5.cu compiled with -DT5_EXP=n (see the kernel source)
+# ablation builds of the library: message_t5.cu compiled with -DT5_EXP=n (1..6, see the kernel source); time with
+#   ADK_LIB=adsorbdiff_b200/lib/libadsorbdiff_b200_exp$n.so T5_TIME_ONLY=1 python scripts/t5_check.py 1024
 set -e
 cd "$(dirname "$0")/../adsorbdiff_b200/csrc"
 for n in "$@"; do
