@@ -221,6 +221,35 @@ def test_train_step_on_one_system_and_on_a_large_one(net):
     step.check_gemm_status()
 
 
+def test_training_under_a_real_ddp_wrapper(net):
+    """The reference wraps the model in DistributedDataParallel (base_trainer.py:442-447) and calls `self.model(batch)`,
+    its own loss and `loss.backward()`: the custom autograd Functions must behave under DDP's hooks, and the gradients
+    must equal those of the bare module."""
+    import torch.distributed as dist
+
+    b = CASES["jit2"][0]().to("cuda:0")
+    G = torch.randn(b.pos.shape[0], 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    net.train()
+    f1, f2 = net(b)
+    ((f1 * G).sum() + (f2 * G).sum()).backward()
+    want = {k: q.grad.clone() for k, q in net.named_parameters() if q.grad is not None}
+    net.zero_grad(set_to_none=True)
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29578", rank=0, world_size=1)
+        created = True
+    try:
+        ddp = torch.nn.parallel.DistributedDataParallel(net, device_ids=[0], find_unused_parameters=True)
+        d1, d2 = ddp(b)
+        ((d1 * G).sum() + (d2 * G).sum()).backward()
+        for k, q in net.named_parameters():
+            if k in want:
+                assert torch.equal(q.grad, want[k]), k
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
 def test_malformed_batch_raises_before_the_optimizer_step(net):
     optim = dict(lr_initial=1e-4, denoising_pos_params=PARAMS)
     step = T.TrainStep(net, optim, T.IGSO3Tables("cuda:0", n_eps=50, x_n=100, L=200))
