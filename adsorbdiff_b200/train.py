@@ -489,6 +489,38 @@ def tr_so3_schedule(batch, params: dict, tables: IGSO3Tables, generator=None, dr
     return batch
 
 
+@torch.no_grad()
+def ads_com_gaussian_schedule(batch, params: dict, generator=None, draws: Optional[dict] = None):
+    """Noising for the translation-only model (`so3_denoising=False`; sde_denoising_trainer.py:138-177): the adsorbate's
+    centre is moved by N(0, sigma^2) in xy, wrapped into the cell (`solve(cell, c)`, `% 1` twice -- the reference's
+    arithmetic, not the transposed solve of `pbc_correction`), lifted by 1 A, and EVERY adsorbate atom is placed at that
+    point (the model only learns the centre of mass)."""
+    dev = batch.pos.device
+    B = int(batch.natoms.shape[0])
+    d = draws or {}
+    t = d["t"] if "t" in d else torch.rand(B, device=dev, generator=generator)
+    tr_sigma = params["ads_std_low"] ** (1 - t) * params["ads_std_high"] ** t
+    ads = batch.tags == 2
+    seg = batch.batch[ads]
+    center = _segment_mean(batch.pos[ads], seg, B)
+    noise = (d["normal"] if "normal" in d else torch.randn(B, 3, device=dev, generator=generator)) * tr_sigma[:, None]
+    noise[:, -1] = 0
+    center = center + noise
+    cell = batch.cell.reshape(B, 3, 3)
+    frac = torch.linalg.solve(cell, center[:, :, None]).squeeze(2)
+    frac = frac % 1
+    frac = frac % 1
+    center = torch.einsum("bi,bij->bj", frac, cell.transpose(1, 2))
+    center[:, -1] += 1
+    pos = batch.pos.clone()
+    pos[ads] = center[seg]
+    batch.pos = pos
+    batch.tr_sigma = tr_sigma[:, None]
+    batch.ads_center_noise_vec = noise
+    batch.tr_score = -noise / tr_sigma[:, None] ** 2
+    return batch
+
+
 def denoising_loss(out, batch, tables: Optional[IGSO3Tables], denoising_pos_coefficient: float = 1.0):
     """`DenoisingTrainer._compute_loss` (:675-728): adsorbate-mean of the two heads, divided by sigma; translation
     term weighted by sigma^2 with z zeroed, rotation term divided by the expected score norm; both `.mean()`s are
@@ -564,7 +596,7 @@ class TrainStep:
             if net.so3_denoising:
                 batch = tr_so3_schedule(batch, self.pos_params, self.tables, self.generator)
             else:
-                raise NotImplementedError("ads_COM_gaussian_schedule (so3_denoising=False) is not built")
+                batch = ads_com_gaussian_schedule(batch, self.pos_params, self.generator)
         out = forward_train(net, batch, check=False)
         loss = denoising_loss(out, batch, self.tables)
         self.optimizer.zero_grad(set_to_none=True)

@@ -124,6 +124,7 @@ def main():
 
     sampler_goldens(ns, model)
     training_goldens(ns)
+    com_schedule_goldens(ns)
 
 
 def run_reference_sampler(ns, model, b, params, seed):
@@ -285,6 +286,25 @@ def training_goldens(ns):
         print(f"train_{case}: loss {float(loss):.6f}")
 
 
+def com_schedule_goldens(ns):
+    """`ads_COM_gaussian_schedule` (sde_denoising_trainer.py:138-177, the translation-only model's noising) run from the
+    reference's text on two seeded batches."""
+    fns, _ = _reference_functions(["ads_COM_gaussian_schedule"])
+    from tests.cases import CASES
+    for case, seed in (("jit2", 21), ("mixed", 22)):
+        b = CASES[case][0]()
+        B = b.num_graphs
+        torch.manual_seed(seed)
+        t = torch.rand(B)
+        normal = torch.zeros(B, 3).normal_()
+        torch.manual_seed(seed)
+        nb = fns["ads_COM_gaussian_schedule"](b, dict(TRAIN_PARAMS))
+        np.savez_compressed(os.path.join(OUT, f"train_com_{case}.npz"), seed=np.array(seed), t=t.numpy(),
+                            normal=normal.numpy(), pos=nb.pos.numpy(), tr_sigma=nb.tr_sigma.numpy(),
+                            tr_score=nb.tr_score.numpy(), ads_center_noise_vec=nb.ads_center_noise_vec.numpy())
+        print(f"train_com_{case}: ok")
+
+
 if __name__ == "__main__":
     import argparse
 
@@ -292,8 +312,11 @@ if __name__ == "__main__":
     ap.add_argument("--sampler-only", nargs="*", default=None,
                     help="regenerate only the named sampler fixtures (e.g. sampler100 sampler_sde)")
     ap.add_argument("--training-only", action="store_true", help="regenerate only igso3.npz / train_*.npz")
+    ap.add_argument("--com-only", action="store_true", help="regenerate only train_com_*.npz")
     a = ap.parse_args()
-    if a.training_only:
+    if a.com_only:
+        com_schedule_goldens(ref_import.load())
+    elif a.training_only:
         training_goldens(ref_import.load())
     elif a.sampler_only is not None:
         ns_ = ref_import.load()

@@ -125,6 +125,20 @@ def test_noising_and_loss_match_reference(tables, case):
     np.testing.assert_allclose(float(lo), float(ref["loss"]), rtol=1e-5)
 
 
+@pytest.mark.parametrize("case", ["jit2", "mixed"])
+def test_com_only_noising_matches_reference(case):
+    """`ads_COM_gaussian_schedule` (the so3_denoising=False variant) with the reference's draws injected."""
+    ref = np.load(os.path.join(GOLDEN, f"train_com_{case}.npz"))
+    b = CASES[case][0]()
+    pos0 = b.pos.clone()
+    nb = T.ads_com_gaussian_schedule(b, PARAMS, draws=dict(t=torch.tensor(ref["t"]), normal=torch.tensor(ref["normal"])))
+    assert torch.equal(nb.pos[b.tags != 2], pos0[b.tags != 2])
+    np.testing.assert_allclose(nb.tr_sigma.numpy(), ref["tr_sigma"], rtol=1e-6)
+    np.testing.assert_allclose(nb.ads_center_noise_vec.numpy(), ref["ads_center_noise_vec"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(nb.tr_score.numpy(), ref["tr_score"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(nb.pos.numpy(), ref["pos"], atol=2e-5)
+
+
 def test_schedule_statistics(tables):
     """Size-independent properties of the random path: sigma ranges, xy-only translation, rigid adsorbate."""
     b = CASES["mixed"][0]()
