@@ -353,6 +353,10 @@ class IGSO3Tables:
 
     def __init__(self, device="cpu", min_eps=0.01, max_eps=2.0, n_eps=1000, x_n=2000, L=2000):
         self.min_eps, self.max_eps, self.n_eps, self.x_n = float(min_eps), float(max_eps), int(n_eps), int(x_n)
+        # the series' terms decay like exp(-l^2 eps^2): below L ~ 6 / eps the narrowest table rows are not converged
+        # (negative densities, NaN scores).  The reference's L = 2000 covers its min_eps = 0.01 (6 / eps = 600).
+        if L * float(min_eps) < 6.0:
+            raise ValueError(f"IGSO3Tables: L={L} terms do not converge the series at min_eps={min_eps} (need L >= {6.0 / float(min_eps):.0f})")
         dev = torch.device(device)
         f64 = dict(dtype=torch.float64, device=dev)
         eps = 10 ** torch.linspace(math.log10(min_eps), math.log10(max_eps), n_eps, **f64)
@@ -557,6 +561,32 @@ def allreduce_mean_(tensors) -> None:
         o += t.numel()
 
 
+class ShadowEma:
+    """The slice of `ExponentialMovingAverage` (modules/exponential_moving_average.py:20-130) the trainer and the sampler
+    use: `update`, `store`, `copy_to`, `restore` -- the sampler swaps the shadow weights in for a run
+    (sde_denoising_trainer.py:580-583, 650-651)."""
+
+    def __init__(self, params, decay: float):
+        self.params, self.decay = list(params), float(decay)
+        self.shadow_params = [q.detach().clone() for q in self.params]
+        self.collected_params = []
+
+    def update(self) -> None:
+        torch._foreach_lerp_(self.shadow_params, [q.detach() for q in self.params], 1.0 - self.decay)
+
+    def store(self) -> None:
+        self.collected_params = [q.detach().clone() for q in self.params]
+
+    def copy_to(self) -> None:
+        for s_, q in zip(self.shadow_params, self.params):
+            q.data.copy_(s_)
+
+    def restore(self) -> None:
+        for c, q in zip(self.collected_params, self.params):
+            q.data.copy_(c)
+        self.collected_params = []
+
+
 class TrainStep:
     """noise -> forward -> loss -> backward -> (all-reduce) -> clip -> AdamW -> EMA; the body of
     `DenoisingTrainer.train` (:409-447) + `_backward` (base_trainer.py:787-820) with the optimizer set up as
@@ -583,7 +613,9 @@ class TrainStep:
         self.optimizer = torch.optim.AdamW(groups, lr=float(optim.get("lr_initial", 1e-4)), fused=dev.type == "cuda", **extra)
         self.clip = optim.get("clip_grad_norm")
         self.ema_decay = optim.get("ema_decay")
-        self.shadow = [q.detach().clone() for q in self.params] if self.ema_decay else None
+        self.ema = ShadowEma(self.params, self.ema_decay) if self.ema_decay else None   # what `Denoiser` / `ml_diffuse` look for
+        self.shadow = self.ema.shadow_params if self.ema else None
+        self._unwrapped_model = net                                                      # trainer-like: unwrap_model(step)
         self.pos_params = optim.get("denoising_pos_params", {})
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.step_count = 0
@@ -607,12 +639,22 @@ class TrainStep:
         if self.clip:
             torch.nn.utils.clip_grad_norm_(self.params, max_norm=float(self.clip), foreach=True)
         self.optimizer.step()
-        if self.shadow is not None:   # ExponentialMovingAverage.update (exponential_moving_average.py:71-97)
-            torch._foreach_lerp_(self.shadow, [q.detach() for q in self.params], 1.0 - float(self.ema_decay))
+        if self.ema is not None:   # ExponentialMovingAverage.update (exponential_moving_average.py:71-97)
+            self.ema.update()
         self.step_count += 1
         if self.status_every and self.step_count % self.status_every == 0:
             self.check_gemm_status()
         return loss.detach()
+
+    @torch.no_grad()
+    def predict_denoising(self, batch, per_image: bool = False, disable_tqdm: bool = True) -> dict:
+        """`DenoisingTrainer.predict_denoising` for one batch (sde_denoising_trainer.py:555-673, without its per-call EMA
+        swap: the sampler swaps once per run): makes this object usable wherever the sampler takes a trainer."""
+        self.net.eval()
+        out = self.net(batch)
+        if self.net.so3_denoising:
+            return {"positions": out[0], "positions_free": out[1]}
+        return {"positions": out}
 
     def check_gemm_status(self) -> None:
         """The tensor-core GEMMs pick their prescales from the operands' own maxima, so the fp16 range can only be

@@ -8,7 +8,7 @@ import bench
 dev = torch.device("cuda:0")
 net = PaiNN(None, 0, 1, so3_denoising=True).to(dev)
 net.load_state_dict(S.random_state_dict(0), strict=True)
-step = T.TrainStep(net, bench.TRAIN_OPTIM, T.IGSO3Tables(dev, n_eps=200, x_n=400, L=400))
+step = T.TrainStep(net, bench.TRAIN_OPTIM, T.IGSO3Tables(dev))
 B = 48
 for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     print(float(step(S.collate([S.make_system(i * B + k) for k in range(B)]).to(dev))))

@@ -208,12 +208,19 @@ def test_train_step_reduces_loss_and_updates_ema(net):
     with torch.no_grad():
         f1, f2 = net(S.make_batch(2).to("cuda:0"))
     assert torch.isfinite(f1).all() and torch.isfinite(f2).all()
+    # the step object is trainer-like for the sampler: `ml_diffuse(model=step)` swaps the EMA weights in and out
+    from adsorbdiff_b200 import ml_diffuse
+    w_live = net.message_layers[0].rbf_proj.weight.detach().clone()
+    out = ml_diffuse(batch=S.make_batch(2, first_id=70).to("cuda:0"), model=step,
+                     denoising_pos_params=dict(PARAMS, num_steps=3, early_stop=False), traj_dir=None, save_full_traj=False,
+                     device="cuda:0")
+    assert torch.isfinite(out.pos).all() and torch.equal(w_live, net.message_layers[0].rbf_proj.weight)
 
 
 def test_train_step_on_one_system_and_on_a_large_one(net):
     """Degenerate batch shapes of the step: a single system (one row chunk per few rows, GEMMs on the narrow tiles) and a
     218-atom slab (more rows than any sampler test, row degree up to 100)."""
-    tables = T.IGSO3Tables("cuda:0", n_eps=100, x_n=200, L=300)
+    tables = T.IGSO3Tables("cuda:0")   # (a truncated series, e.g. L = 300, is not converged at rot_sigma = 0.01: NaN scores)
     step = T.TrainStep(net, dict(lr_initial=1e-6, denoising_pos_params=PARAMS, clip_grad_norm=100), tables)
     for batch in (S.make_batch(1), S.collate([S.make_system(31, size=(6, 6, 6)), S.make_system(2)])):
         losses = [float(step(batch.clone().to("cuda:0"))) for _ in range(2)]
@@ -252,7 +259,7 @@ def test_training_under_a_real_ddp_wrapper(net):
 
 def test_malformed_batch_raises_before_the_optimizer_step(net):
     optim = dict(lr_initial=1e-4, denoising_pos_params=PARAMS)
-    step = T.TrainStep(net, optim, T.IGSO3Tables("cuda:0", n_eps=50, x_n=100, L=200))
+    step = T.TrainStep(net, optim, T.IGSO3Tables("cuda:0"))
     b = CASES["empty"][0]().to("cuda:0")
     w0 = net.out_forces.output_network[1].vec2_proj.weight.detach().clone()
     with pytest.raises(ValueError):
