@@ -620,6 +620,10 @@ class TrainStep:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.step_count = 0
         self.status_every = int(optim.get("status_every", 50))   # host read of the GEMMs' overflow word (one sync)
+        # loss read-out without draining the stream: each step copies its loss to a pinned ring slot right after the
+        # forward and records an event; `read_loss(lag)` waits for that event only
+        self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == "cuda" else None
+        self._loss_events = [torch.cuda.Event() for _ in range(4)] if dev.type == "cuda" else None
 
     def __call__(self, batch, noised: bool = False) -> torch.Tensor:
         net = self.net
@@ -631,6 +635,10 @@ class TrainStep:
                 batch = ads_com_gaussian_schedule(batch, self.pos_params, self.generator)
         out = forward_train(net, batch, check=False)
         loss = denoising_loss(out, batch, self.tables)
+        if self._loss_host is not None:
+            slot = self.step_count % 4
+            self._loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            self._loss_events[slot].record()
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
         check_status_async(net, net._train_plan)   # raises before the optimizer sees gradients of a malformed batch
@@ -645,6 +653,16 @@ class TrainStep:
         if self.status_every and self.step_count % self.status_every == 0:
             self.check_gemm_status()
         return loss.detach()
+
+    def read_loss(self, lag: int = 0) -> float:
+        """Loss of the step made `lag` calls ago (0 = the last one, up to 3) as a Python float.  Waits for that step's
+        forward only, not for the stream: logging the previous step's loss while the current step runs keeps the GPU fed
+        (the reference's `loss.item()` right after `backward()` drains it every step)."""
+        k = self.step_count - 1 - lag
+        if k < 0 or lag > 3:
+            raise ValueError("no such step")
+        self._loss_events[k % 4].synchronize()
+        return float(self._loss_host[k % 4])
 
     @torch.no_grad()
     def predict_denoising(self, batch, per_image: bool = False, disable_tqdm: bool = True) -> dict:

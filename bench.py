@@ -653,7 +653,8 @@ def run_train(args):
     """`python bench.py --train`: the optimisation step of SURVEY.md section 8 row f-1 at the reference's batch size
     (48 systems per GPU, weak scaling: data parallel, one gradient all-reduce per step).  A step = noising
     (tr_so3_schedule) + forward + loss + backward + all-reduce + clip + AdamW + EMA, on a batch copied from pinned
-    host memory inside the timed region, loss read back every step (the reference logs `loss.item()` every step)."""
+    host memory inside the timed region, every step's loss read on the host (one step late; the reference logs
+    `loss.item()` every step)."""
     import torch.distributed as dist
 
     from adsorbdiff_b200 import PaiNN, synthetic as S, train as T
@@ -682,7 +683,11 @@ def run_train(args):
     losses = []
 
     def one(i):
-        losses.append(float(step(hosts[i % len(hosts)].to(dev, non_blocking=True))))
+        # every step's loss is read on the host (the reference logs loss.item() every step) -- one step late, through
+        # TrainStep.read_loss, so that the read does not drain the stream the next step is already queued on
+        step(hosts[i % len(hosts)].to(dev, non_blocking=True))
+        if step.step_count > 1:
+            losses.append(step.read_loss(lag=1))
 
     def barrier():
         if world > 1:
@@ -700,6 +705,7 @@ def run_train(args):
     e0.record()
     for i in range(args.steps):
         one(i)
+    losses.append(step.read_loss(lag=0))   # the last step's loss: inside the timed region as well
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
