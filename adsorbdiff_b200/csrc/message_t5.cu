@@ -46,11 +46,21 @@ constexpr int T5_SF = 64;                                     // features per CT
 constexpr int T5_TILE = 128;                                  // columns (edge slots) per tile = MMA N
 constexpr int T5_ROWS = 8;                                    // target rows per tile
 constexpr int T5_SLOT = 16;                                   // columns per row
-constexpr int T5_DSLOTS = 4;                                  // TMEM accumulator ring (4 x 128 columns = all of TMEM)
-constexpr int T5_BBUFS = 2;                                   // operand-tile buffers
-static_assert(T5_BBUFS % T5_GEN_GROUPS == 0, "each generator group owns T5_BBUFS / T5_GEN_GROUPS operand buffers");
+// T5_WTMEM (default): the weight tile is the TMEM-resident A operand of the MMA (columns 384..511: hi plane | lo
+// plane, a lane = a weight row, two fp16 per column), written once per phase with tcgen05.st by one epilogue
+// warpgroup.  The tensor core then fetches only the rbf tile from shared memory (half the operand wavefronts of the
+// shared-memory variant), no weight TMA / swizzle is needed, and the 64 KB the weights occupied hold two more operand
+// buffers.  Price: three accumulator slots instead of four.  -DT5_WTMEM=0 builds the round-2 shared-memory variant.
+#ifndef T5_WTMEM
+#define T5_WTMEM 1
+#endif
+constexpr int T5_DSLOTS = T5_WTMEM ? 3 : 4;                   // TMEM accumulator ring of 128-column slots
+// operand-tile buffers: a kernel template parameter.  T5_WTMEM: 4 (two per generator group) while the system's
+// sources leave room for them (up to 111 atoms at F = 512), 2 for larger systems (up to 200 atoms); else 2.
+constexpr int T5_BBUFS_MAX = T5_WTMEM ? 4 : 2;
+constexpr uint32_t T5_W_TMEM_COL = 384;                       // T5_WTMEM: first column of the weight planes (64 + 64)
 constexpr int T5_MAX_TILES = 512;
-constexpr int T5_MAX_ATOMS = 128;
+constexpr int T5_MAX_ATOMS = T5_WTMEM ? 200 : 128;
 constexpr uint32_t T5_W_KBLOCK = 128 * 128;                   // [128 rows][64 centres] fp16, 128-byte rows
 constexpr uint32_t T5_W_PLANE = 2 * T5_W_KBLOCK;
 constexpr uint32_t T5_W_BYTES = 2 * T5_W_PLANE;               // hi + lo: 64 KB
@@ -66,9 +76,13 @@ constexpr float T5_RBF_SCALE = 1024.0f;
 
 // optional pipeline trace (debug builds: -DT5_TRACE): clock64 stamps of CTA (0,0,0), phase 0, [tile][16 events]
 #ifdef T5_TRACE
+#ifndef T5_TRACE_X
+#define T5_TRACE_X 0   // the traced CTA: slice T5_TRACE_X of system T5_TRACE_Y (first-wave CTAs see cold caches)
+#define T5_TRACE_Y 0
+#endif
 __device__ long long g_t5_trace[T5_MAX_TILES * 16];
-#define T5_STAMP(ti, ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && phase == 0 && lane == 0) g_t5_trace[(ti) * 16 + (ev)] = clock64(); } while (0)
-#define T5_CTA_STAMP(ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_t5_trace[(T5_MAX_TILES - 1) * 16 + (ev)] = clock64(); } while (0)
+#define T5_STAMP(ti, ev) do { if (blockIdx.x == T5_TRACE_X && blockIdx.y == T5_TRACE_Y && blockIdx.z == 0 && phase == 0 && lane == 0) g_t5_trace[(ti) * 16 + (ev)] = clock64(); } while (0)
+#define T5_CTA_STAMP(ev) do { if (blockIdx.x == T5_TRACE_X && blockIdx.y == T5_TRACE_Y && blockIdx.z == 0 && threadIdx.x == 0) g_t5_trace[(T5_MAX_TILES - 1) * 16 + (ev)] = clock64(); } while (0)
 #else
 #define T5_STAMP(ti, ev) do { } while (0)
 #define T5_CTA_STAMP(ev) do { } while (0)
@@ -85,6 +99,7 @@ struct T5Params {
     const float* vec_in;
     const float* b_rbf;
     const float* rbf_offset;
+    const __half* w_split;      // [2 planes][3F][R] fp16 (hi, lo) of s_w * rbf_proj.weight
     int F, R, n_max;
     float inv_cutoff, coeff_sqrt, env_a, env_b, env_c;
     int env_p;
@@ -97,12 +112,18 @@ struct T5Params {
     uint32_t* status;
 };
 
-__host__ __device__ inline size_t t5_fixed_bytes() {
-    return T5_W_BYTES + T5_BBUFS * T5_B_BYTES + T5_DSLOTS * T5_META_BYTES + 512 /*barriers, item meta, windows*/ +
+__host__ __device__ inline size_t t5_fixed_bytes(int nbufs) {
+    return (T5_WTMEM ? 0 : T5_W_BYTES) + nbufs * T5_B_BYTES + T5_DSLOTS * T5_META_BYTES + 512 /*barriers, item meta, windows*/ +
            T5_MAX_TILES * 4 + 2 * T5_MAX_ATOMS /*row order*/ + 128 /*mu*/ * 4 + 2 * 4 * T5_MAX_ATOMS /*row start, degree*/;
 }
-__host__ __device__ inline size_t t5_smem_bytes(int n_max) {
-    return 1024 /*alignment slack*/ + t5_fixed_bytes() + (size_t)(n_max + 1) * T5_SRC_PITCH_B;
+__host__ __device__ inline size_t t5_smem_bytes(int n_max, int nbufs) {
+    return 1024 /*alignment slack*/ + t5_fixed_bytes(nbufs) + (size_t)(n_max + 1) * T5_SRC_PITCH_B;
+}
+// the deepest operand ring whose shared memory still fits a system of n_max atoms (0: none does)
+inline int t5_pick_bufs(int n_max) {
+    for (int nb = T5_BBUFS_MAX; nb >= 2; nb -= 2)
+        if (t5_smem_bytes(n_max, nb) <= 227 * 1024) return nb;
+    return 0;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -229,53 +250,103 @@ __device__ __forceinline__ void tile_body(uint32_t t_addr, const uint8_t* meta, 
     }
 }
 
-// Sources of one phase into shared memory (all threads): A = [atom][xh1 (64) | xh3 (64)], B = [atom][p2x | p2y | p2z]
-// with p2c = xh2 * vec_c; row n = zeros (what padding columns read).
-__device__ __forceinline__ void stage_sources(const T5Params& P, float* s_src, int phase, int a0, int n, int f0) {
-    float4* s_src4 = reinterpret_cast<float4*>(s_src);
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+// Sources of one phase into shared memory: A = [atom][xh1 (64) | xh3 (64)], B = [atom][p2x | p2y | p2z] with
+// p2c = xh2 * vec_c; row n = zeros (what padding columns read).  Staging is latency bound (a few 16-byte items per
+// thread, each a round trip to L2 / HBM), so every thread issues the loads of BATCH items before it stores any:
+// `tid` of `nthreads` callers, items tid + k * nthreads from `first` on.
+__device__ __forceinline__ float4 stage_load_a(const T5Params& P, int i, int total, int a0, int n, int f0) {
     constexpr int Q = T5_SF / 4;   // float4 per 64-feature row
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < total) {
+        const int j = i / (2 * Q), r = i - j * 2 * Q;
+        const int g = r >= Q ? 2 : 0, q4 = r & (Q - 1);
+        if (j < n) v = *reinterpret_cast<const float4*>(P.xh + (size_t)(a0 + j) * 3 * P.F + g * P.F + f0 + 4 * q4);
+    }
+    return v;
+}
+template <int BATCH>
+__device__ __forceinline__ void stage_sources(const T5Params& P, float* s_src, int phase, int a0, int n, int f0, int tid,
+                                              int nthreads, int first = 0) {
+    float4* s_src4 = reinterpret_cast<float4*>(s_src);
+    constexpr int Q = T5_SF / 4;
     const int F = P.F;
     if (phase == 0) {
-        for (int i = threadIdx.x; i < (n + 1) * 2 * Q; i += T5_THREADS) {
-            const int j = i / (2 * Q), r = i - j * 2 * Q;
-            const int g = r >= Q ? 2 : 0, q4 = r & (Q - 1);
-            s_src4[i] = j < n ? *reinterpret_cast<const float4*>(P.xh + (size_t)(a0 + j) * 3 * F + g * F + f0 + 4 * q4) : zero4;
+        const int total = (n + 1) * 2 * Q;
+        for (int i0 = first + tid; i0 < total; i0 += BATCH * nthreads) {
+            float4 v[BATCH];
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) v[k] = stage_load_a(P, i0 + k * nthreads, total, a0, n, f0);
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k)
+                if (i0 + k * nthreads < total) s_src4[i0 + k * nthreads] = v[k];
         }
     } else {
-        for (int i = threadIdx.x; i < (n + 1) * 3 * Q; i += T5_THREADS) {
-            const int j = i / (3 * Q), r = i - j * 3 * Q;
-            const int c = r / Q, q4 = r - c * Q;
-            float4 v = zero4;
-            if (j < n) {
-                const float4 a = *reinterpret_cast<const float4*>(P.xh + (size_t)(a0 + j) * 3 * F + F + f0 + 4 * q4);
-                const float4 w = *reinterpret_cast<const float4*>(P.vec_in + ((size_t)(a0 + j) * 3 + c) * F + f0 + 4 * q4);
-                v = make_float4(a.x * w.x, a.y * w.y, a.z * w.z, a.w * w.w);
+        const int total = (n + 1) * 3 * Q;
+        for (int i0 = first + tid; i0 < total; i0 += BATCH * nthreads) {
+            float4 a[BATCH], w[BATCH];
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+                const int i = i0 + k * nthreads;
+                a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                w[k] = a[k];
+                if (i < total) {
+                    const int j = i / (3 * Q), r = i - j * 3 * Q;
+                    const int c = r / Q, q4 = r - c * Q;
+                    if (j < n) {
+                        a[k] = *reinterpret_cast<const float4*>(P.xh + (size_t)(a0 + j) * 3 * F + F + f0 + 4 * q4);
+                        w[k] = *reinterpret_cast<const float4*>(P.vec_in + ((size_t)(a0 + j) * 3 + c) * F + f0 + 4 * q4);
+                    }
+                }
             }
-            s_src4[i] = v;
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k)
+                if (i0 + k * nthreads < total)
+                    s_src4[i0 + k * nthreads] = make_float4(a[k].x * w[k].x, a[k].y * w[k].y, a[k].z * w[k].z, a[k].w * w[k].w);
         }
     }
 }
+#if T5_WTMEM
+// weight rows of one phase: global -> registers (eight 16-byte loads), registers -> TMEM (see the kernel's set-up)
+__device__ __forceinline__ void load_weight_rows(const T5Params& P, uint4* w4, int phase, int warp, int lane, int f0) {
+    const int r = (warp & 3) * 32 + lane, wg = (warp - T5_EPI_WARP0) >> 2;
+    const int g = phase == 0 ? (r < 64 ? 0 : 2) : 1;
+    const uint4* wrow = reinterpret_cast<const uint4*>(P.w_split + (((size_t)(wg >> 1) * 3 + g) * P.F + f0 + (r & 63)) * P.R) + (wg & 1) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w4[i] = __ldg(wrow + i);
+}
+__device__ __forceinline__ void store_weight_rows(uint32_t tmem_base, const uint4* w4, int warp) {
+    const int wg = (warp - T5_EPI_WARP0) >> 2;
+    const uint32_t t_w = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + T5_W_TMEM_COL + (uint32_t)((wg >> 1) * 64 + (wg & 1) * 32);
+    tmem_st16(t_w, reinterpret_cast<const uint32_t*>(w4));
+    tmem_st16(t_w + 16u, reinterpret_cast<const uint32_t*>(w4 + 4));
+    tmem_st_wait();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+#endif
+constexpr int T5_STAGE_PRE = 3;   // phase-A items per thread whose loads are in flight during the CTA's set-up
 
+template <int T5_BBUFS>
 __global__ void __launch_bounds__(T5_THREADS, 1)
-message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
+message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {   // (tmW: shared-memory weight variant only)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t w_smem = base;
-    const uint32_t b_smem = base + T5_W_BYTES;
+    const uint32_t w_smem = base;   // (shared-memory weight variant only)
+    const uint32_t b_smem = base + (T5_WTMEM ? 0u : T5_W_BYTES);
     const uint32_t meta_smem = b_smem + T5_BBUFS * T5_B_BYTES;
     const uint32_t ctl = meta_smem + T5_DSLOTS * T5_META_BYTES;     // 512-byte control block
     uint8_t* ctl_g = gbase + (ctl - base);
     const uint32_t w_full = ctl;
+    static_assert(T5_BBUFS <= 4 && T5_DSLOTS <= 4, "control block layout");
+    static_assert(T5_BBUFS % T5_GEN_GROUPS == 0, "each generator group owns T5_BBUFS / T5_GEN_GROUPS operand buffers");
     auto b_full = [&](int s) { return ctl + 8u + 8u * s; };
-    auto b_empty = [&](int s) { return ctl + 24u + 8u * s; };
-    auto d_full = [&](int s) { return ctl + 40u + 8u * s; };
-    auto d_empty = [&](int s) { return ctl + 72u + 8u * s; };
-    auto m_full = [&](int s) { return ctl + 104u + 8u * s; };
-    const uint32_t tmem_slot = ctl + 136u;
-    int* s_item = reinterpret_cast<int*>(ctl_g + 144);             // [T5_BBUFS][4]: kbase, nks, last, -
-    int* s_win = reinterpret_cast<int*>(ctl_g + 176);              // [groups 2][parity 2][4 warps][2]: (kmin, kmax)
+    auto b_empty = [&](int s) { return ctl + 40u + 8u * s; };
+    auto d_full = [&](int s) { return ctl + 72u + 8u * s; };
+    auto d_empty = [&](int s) { return ctl + 104u + 8u * s; };
+    auto m_full = [&](int s) { return ctl + 136u + 8u * s; };
+    const uint32_t tmem_slot = ctl + 168u;
+    int* s_item = reinterpret_cast<int*>(ctl_g + 176);             // [T5_BBUFS][4]: kbase, nks, last, -
+    int* s_win = reinterpret_cast<int*>(ctl_g + 240);              // [groups 2][parity 2][4 warps][2]: (kmin, kmax)
     int* s_ntiles = reinterpret_cast<int*>(ctl_g + 496);
     uint32_t* s_tiles = reinterpret_cast<uint32_t*>(ctl_g + 512);
     int16_t* s_order = reinterpret_cast<int16_t*>(ctl_g + 512 + T5_MAX_TILES * 4);
@@ -292,12 +363,21 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
     const bool has_vec = P.vec_in != nullptr;
     if (n > P.n_max) return;   // larger than the staging area this launch was sized for: another kernel owns it (row_sel == 0 there)
     T5_CTA_STAMP(0);
+    // phase A's sources: the first T5_STAGE_PRE items of every thread are requested now and stored after the set-up
+    // below (row ranking, tile list), which hides one of the two staging round trips behind the other work
+    float4 pre[T5_STAGE_PRE];
+#pragma unroll
+    for (int k = 0; k < T5_STAGE_PRE; ++k)
+        pre[k] = stage_load_a(P, (int)threadIdx.x + k * T5_THREADS, (n + 1) * 2 * (T5_SF / 4), a0, n, f0);
+
 
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (warp == 0) {
         if (lane == 0) {
+#if !T5_WTMEM
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
             mbar_init(w_full, 1);
+#endif
             for (int s = 0; s < T5_BBUFS; ++s) { mbar_init(b_full(s), 4); mbar_init(b_empty(s), 1); }
             for (int s = 0; s < T5_DSLOTS; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 4 * T5_TEAM_WG); mbar_init(m_full(s), 4); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -347,6 +427,11 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
             }
         }
     }
+#pragma unroll
+    for (int k = 0; k < T5_STAGE_PRE; ++k)
+        if ((int)threadIdx.x + k * T5_THREADS < (n + 1) * 2 * (T5_SF / 4))
+            reinterpret_cast<float4*>(s_src)[threadIdx.x + k * T5_THREADS] = pre[k];
+    stage_sources<2>(P, s_src, 0, a0, n, f0, (int)threadIdx.x, T5_THREADS, T5_STAGE_PRE * T5_THREADS);   // (systems > 83 atoms)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -385,8 +470,9 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
     if (warp < T5_GEN_WARP0) {
         // ===================== warpgroup 0: TMA (weights) + MMA issue =====================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        uint32_t items[T5_BBUFS] = {0u, 0u};   // operand tiles consumed per buffer (= per generator group)
+        uint32_t item_par = 0u;   // bit b: parity of the number of operand tiles consumed from buffer b
         for (int phase = 0; phase < nphases; ++phase) {
+#if !T5_WTMEM
             if (warp == 0 && lane == 0) {
                 mbar_expect_tx(w_full, T5_W_BYTES);
                 const int g_lo = phase == 0 ? 0 : 1, g_hi = phase == 0 ? 2 : 1;   // row halves: [m1 | m3] or [m2 | m2]
@@ -399,14 +485,22 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                         tma_load_2d(dst + 64 * 128, &tmW, w_full, kb * 64, pl * 3 * F + g_hi * F + f0);
                     }
             }
-            stage_sources(P, s_src, phase, a0, n, f0);
+#endif
+            // (phase A's sources were staged during the set-up, phase B's are staged by the other roles' 768 threads:
+            // this warpgroup runs on 40 registers)
             __syncthreads();
             T5_CTA_STAMP(2 + 3 * phase);
             if (warp == 0 && lane == 0) {
                 const uint32_t tile0 = (uint32_t)phase * (uint32_t)ntiles;
                 const uint32_t idesc = (1u << 4) | ((uint32_t)(T5_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+#if T5_WTMEM
+                // the weight planes were written to TMEM by an epilogue warpgroup before the barrier above
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t wh_col = tmem_base + T5_W_TMEM_COL;
+#else
                 const uint32_t wh_lo = desc_lo(w_smem);
                 mbar_wait(w_full, phase & 1);
+#endif
                 for (int ti = 0; ti < ntiles; ++ti) {
                     const uint32_t tau = tile0 + ti;
                     const int ds = tau % T5_DSLOTS;
@@ -416,7 +510,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                     bool first = true, last = false;
                     const int buf = ti % T5_BBUFS;
                     while (!last) {
-                        mbar_wait(b_full(buf), items[buf] & 1);
+                        mbar_wait(b_full(buf), (item_par >> buf) & 1u);
                         T5_STAMP(ti, 6);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const int kbase = s_item[buf * 4], nks = s_item[buf * 4 + 1];
@@ -426,18 +520,27 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                         // All descriptor words first (independent integer work), then the tcgen05.mma of the item
                         // in straight-line code per k-step count: the issuing thread, not the tensor pipe, paces a
                         // tile (~100 cycles per MMA when descriptor arithmetic and branches sit between them).
+                        const uint32_t acc0 = first ? 0u : 1u;
+                        // corrections first (while the accumulator is small), then the hi x hi products
+#if T5_WTMEM
+                        // A operand in TMEM: k-step s of the window starts (kbase + 16 s) / 2 columns into a plane
+                        const uint32_t a_col = wh_col + (uint32_t)(kbase >> 1);
+#define T5_MMA_CORR(s, acc)                                                                                         \
+    umma_f16_ts(d_tmem, a_col + 8u * (s), mk_desc(bl_lo + 2 * (s)), idesc, acc);                                    \
+    umma_f16_ts(d_tmem, a_col + 64u + 8u * (s), mk_desc(bh_lo + 2 * (s)), idesc, 1u);
+#define T5_MMA_MAIN(s) umma_f16_ts(d_tmem, a_col + 8u * (s), mk_desc(bh_lo + 2 * (s)), idesc, 1u);
+#else
                         uint32_t a_lo[4];
 #pragma unroll
                         for (int s = 0; s < 4; ++s) {
                             const int k = kbase + 16 * s;
                             a_lo[s] = wh_lo + (uint32_t)(k >> 6) * (T5_W_KBLOCK >> 4) + (uint32_t)((k >> 3) & 7);
                         }
-                        const uint32_t acc0 = first ? 0u : 1u;
-                        // corrections first (while the accumulator is small), then the hi x hi products
 #define T5_MMA_CORR(s, acc)                                                                                         \
     umma_f16(d_tmem, mk_desc(a_lo[s]), mk_desc(bl_lo + 2 * (s)), idesc, acc);                                      \
     umma_f16(d_tmem, mk_desc(a_lo[s] + (T5_W_PLANE >> 4)), mk_desc(bh_lo + 2 * (s)), idesc, 1u);
 #define T5_MMA_MAIN(s) umma_f16(d_tmem, mk_desc(a_lo[s]), mk_desc(bh_lo + 2 * (s)), idesc, 1u);
+#endif
                         if (T5_EXP == 4 || T5_EXP == 6) {
                         } else if (nks == 4) {
                             T5_MMA_CORR(0, acc0) T5_MMA_CORR(1, 1u) T5_MMA_CORR(2, 1u) T5_MMA_CORR(3, 1u)
@@ -456,7 +559,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
 #undef T5_MMA_MAIN
                         umma_commit(b_empty(buf));
                         first = false;
-                        ++items[buf];
+                        item_par ^= 1u << buf;
                     }
                     umma_commit(d_full(ds));
                     T5_STAMP(ti, 7);
@@ -478,8 +581,9 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
         const uint32_t row_off = (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u;
         const float rmax = (float)(R - 1);
         const float h0 = 1.0f / rmax;   // centre spacing (the host checked that rbf_offset is linspace(0, 1, R))
-        uint32_t items[T5_BBUFS] = {0u, 0u};   // operand tiles written per buffer (tile ti uses buffer ti % T5_BBUFS)
-        uint32_t dirty[T5_BBUFS] = {0xffu, 0xffu};   // 16-byte chunks of MY row of a buffer that may hold non-zeros (all, at first)
+        // per operand buffer b (tile ti uses buffer ti % T5_BBUFS; this group owns those with b % T5_GEN_GROUPS == gg):
+        uint32_t item_par = 0u;          // bit b: parity of the number of operand tiles written to it
+        uint32_t dirty = 0xffffffffu;    // byte b: 16-byte chunks of MY row of it that may hold non-zeros (all, at first)
         // the CSR record of this column for tile ti (padding: source row n = zeros)
         auto fetch = [&](int ti, int& src, float4& geo, int& deg_out, int& row_out) {
             src = n;
@@ -502,14 +606,15 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
             }
         };
         for (int phase = 0; phase < nphases; ++phase) {
-            stage_sources(P, s_src, phase, a0, n, f0);
-            __syncthreads();
-            const uint32_t tile0 = (uint32_t)phase * (uint32_t)ntiles;
-            const int pitch = phase == 0 ? (int)T5_SRC_PITCH_A : (int)T5_SRC_PITCH_B;
-            // the record of this group's NEXT tile is in flight while the current one is worked on
+            // the record of this group's NEXT tile is in flight while the current one is worked on; the first one is
+            // requested before the staging and the barrier (a global round trip costs ~3 000 cycles in a busy machine)
             int src1, deg1, row1;
             float4 geo1;
             fetch(gg, src1, geo1, deg1, row1);
+            if (phase > 0) stage_sources<4>(P, s_src, phase, a0, n, f0, (int)threadIdx.x - 128, T5_THREADS - 128);
+            __syncthreads();
+            const uint32_t tile0 = (uint32_t)phase * (uint32_t)ntiles;
+            const int pitch = phase == 0 ? (int)T5_SRC_PITCH_A : (int)T5_SRC_PITCH_B;
             for (int ti = gg; ti < ntiles; ti += T5_GEN_GROUPS) {
                 const uint32_t tau = tile0 + ti, tl = s_tiles[ti];
                 const int ds = tau % T5_DSLOTS;
@@ -583,7 +688,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                 for (int sub = 0; sub < nsub; ++sub) {
                     const int kb = kbase + 64 * sub;
                     const int nks = min(4, nks_total - 4 * sub);
-                    mbar_wait(b_empty(buf), (items[buf] & 1) ^ 1);
+                    mbar_wait(b_empty(buf), ((item_par >> buf) & 1u) ^ 1u);
                     if (gw == 0 && sub == 0) T5_STAMP(ti, 3);
                     const uint32_t bb = b_smem + buf * T5_B_BYTES + row_off;
                     const int q0 = (kb - k8) >> 3;   // my 8-block qq sits in chunk qq - q0 of this operand row
@@ -601,7 +706,8 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                     }
                     // ... and zeros only where this row of the buffer still holds values of an earlier tile (the 16
                     // unconditional zero stores per tile were a tenth of the kernel's shared-memory wavefronts)
-                    const uint32_t stale = dirty[buf] & ~valued & ((1u << (2 * nks)) - 1u);
+                    const uint32_t dirty_b = (dirty >> (8 * buf)) & 0xffu;
+                    const uint32_t stale = dirty_b & ~valued & ((1u << (2 * nks)) - 1u);
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) {
                         if ((stale >> ch) & 1u) {
@@ -610,7 +716,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                             asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr + T5_B_PLANE), "r"(0u) : "memory");
                         }
                     }
-                    dirty[buf] = (dirty[buf] & ~stale) | valued;
+                    dirty = (dirty & ~(0xffu << (8 * buf))) | (((dirty_b & ~stale) | valued) << (8 * buf));
                     if (c == 0) {
                         s_item[buf * 4] = kb;
                         s_item[buf * 4 + 1] = nks;
@@ -620,7 +726,7 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(b_full(buf));
                     if (gw == 0) T5_STAMP(ti, 4);
-                    ++items[buf];
+                    item_par ^= 1u << buf;
                 }
             }
             __syncthreads();
@@ -638,7 +744,19 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
         const float inv_sqrt_h = 1.0f / sqrtf((float)F);
         const float inv_sqrt_3 = 0.57735026918962576451f;
         for (int phase = 0; phase < nphases; ++phase) {
-            stage_sources(P, s_src, phase, a0, n, f0);
+#if T5_WTMEM
+            {
+                // This phase's weight rows into TMEM (all MMAs of the previous phase have retired: its last
+                // __syncthreads came after every epilogue warp's last d_full wait).  Thread = TMEM lane = weight row:
+                // phase A [m1 slice | m3 slice], phase B [m2 slice | m2 slice]; a row is 128 fp16 = 64 columns per
+                // plane, and each of the four epilogue warpgroups writes half a plane.
+                static_assert(T5_EPI_WG == 4, "one (plane, half) per epilogue warpgroup");
+                uint4 wb[8];
+                load_weight_rows(P, wb, phase, warp, lane, f0);
+                store_weight_rows(tmem_base, wb, warp);
+            }
+#endif
+            if (phase > 0) stage_sources<4>(P, s_src, phase, a0, n, f0, (int)threadIdx.x - 128, T5_THREADS - 128);
             __syncthreads();
             const uint32_t tile0 = (uint32_t)phase * (uint32_t)ntiles;
             // phase A: this warpgroup's rows are slots 4 mem .. 4 mem + 3 (lanes 0-63: dx, lanes 64-127: m3 r_hat);
@@ -746,8 +864,8 @@ message_t5_kernel(const __grid_constant__ CUtensorMap tmW, T5Params P) {
 
 extern "C" int64_t adk_message_t5_smem_bytes(int R, int n_max) {
     if (R != 128 || n_max <= 0 || n_max > T5_MAX_ATOMS) return ADK_ERANGE;
-    const size_t bytes = t5_smem_bytes(n_max);
-    return bytes > 227 * 1024 ? (int64_t)ADK_ERANGE : (int64_t)bytes;
+    const int nb = t5_pick_bufs(n_max);
+    return nb == 0 ? (int64_t)ADK_ERANGE : (int64_t)t5_smem_bytes(n_max, nb);
 }
 
 extern "C" int adk_message_t5(const int32_t* atom_off, int B, int n_max, const int32_t* row_sel, const int32_t* row_start,
@@ -762,12 +880,18 @@ extern "C" int adk_message_t5(const int32_t* atom_off, int B, int n_max, const i
         return ADK_EINVAL;
     if (F % T5_SF != 0 || R != 128 || envelope_exponent < 1 || vec_in == vec_out || B > 65535) return ADK_EINVAL;
     if (n_max > T5_MAX_ATOMS) return ADK_ERANGE;
-    const size_t smem = t5_smem_bytes(n_max);
-    if (smem > 227 * 1024) return ADK_ERANGE;
+    const int nbufs = t5_pick_bufs(n_max);
+    if (nbufs == 0) return ADK_ERANGE;
+    const size_t smem = t5_smem_bytes(n_max, nbufs);
     alignas(64) CUtensorMap tmW;
+#if T5_WTMEM
+    memset(&tmW, 0, sizeof(tmW));
+#else
     int rc = make_map_f16(&tmW, w_rbf_split, 2 * 3 * (uint64_t)F, (uint64_t)R, 64, 64);
     if (rc != 0) return rc;
+#endif
     T5Params P;
+    P.w_split = reinterpret_cast<const __half*>(w_rbf_split);
     P.atom_off = atom_off; P.row_sel = row_sel; P.row_start = row_start; P.row_deg = row_deg; P.e_src = e_src;
     P.e_geo = reinterpret_cast<const float4*>(e_geo);
     P.xh = xh; P.vec_in = vec_in; P.b_rbf = b_rbf; P.rbf_offset = rbf_offset;
@@ -789,7 +913,10 @@ extern "C" int adk_message_t5(const int32_t* atom_off, int B, int n_max, const i
     int z = 1;
     while (z < 8 && (long long)B * (F / T5_SF) * z * 2 <= g_num_sms) z *= 2;
     // slices of one system are adjacent in launch order: they run together and share its CSR records in L2
-    message_t5_kernel<<<dim3(F / T5_SF, B, z), T5_THREADS, smem, adk::as_stream(stream)>>>(tmW, P);
+    if (nbufs == T5_BBUFS_MAX)
+        message_t5_kernel<T5_BBUFS_MAX><<<dim3(F / T5_SF, B, z), T5_THREADS, smem, adk::as_stream(stream)>>>(tmW, P);
+    else
+        message_t5_kernel<2><<<dim3(F / T5_SF, B, z), T5_THREADS, smem, adk::as_stream(stream)>>>(tmW, P);
     ADK_LAUNCH_CHECK();
     return 0;
 }
@@ -801,5 +928,8 @@ extern "C" int adk_message_t5_trace(long long* host_out, int n) {
 #endif
 
 int adk_message_t5_set_attrs() {
-    return (int)cudaFuncSetAttribute(message_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    int rc = (int)cudaFuncSetAttribute(message_t5_kernel<T5_BBUFS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (rc == 0 && T5_BBUFS_MAX != 2)
+        rc = (int)cudaFuncSetAttribute(message_t5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return rc;
 }

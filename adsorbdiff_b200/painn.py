@@ -243,6 +243,7 @@ class PaiNN(nn.Module):
         self.msg = "t5"
         self.msg_t5_comp = 0.0  # accumulate-truncation compensation of the t5 kernel
         self.t5_min_ctas = 0   # (bring-up knob: use the t5 kernel only from this many CTAs on)
+        self.t5_max_atoms = None   # (test knob: cap the system size the t5 kernel takes, so the warp-MMA kernel sees work)
         self.msg_comp = 1.1920929e-07  # accumulate-truncation compensation of the message MMA (calibrated)
         self._wsplit_cache: dict = {}
 
@@ -386,6 +387,8 @@ class PaiNN(nn.Module):
             if not ok:
                 return 0
             lo, hi = 0, min(p.n_max, _cabi.MAX_ATOMS_PER_SYSTEM)
+            if fn is lib.adk_message_t5_smem_bytes and self.t5_max_atoms:
+                hi = min(hi, int(self.t5_max_atoms))
             if fn(self.num_rbf, hi) > 0:
                 return hi
             while lo < hi:   # the smem need grows with n: bisect

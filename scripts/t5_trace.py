@@ -6,7 +6,7 @@ import numpy as np
 import torch
 from adsorbdiff_b200 import _cabi
 
-lib = os.path.join(ROOT, "adsorbdiff_b200", "lib", "libadsorbdiff_b200_trace.so")
+lib = os.environ.get("ADK_LIB") or os.path.join(ROOT, "adsorbdiff_b200", "lib", "libadsorbdiff_b200_trace.so")
 _cabi._LIB_PATH = lib
 from adsorbdiff_b200 import PaiNN, synthetic as S
 

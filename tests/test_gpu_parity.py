@@ -263,22 +263,50 @@ def test_large_system_falls_back_and_matches(weights):
         assert float((got.double().cpu() - ref).abs().max() / ref.abs().max()) < FEATURE_TOL
 
 
-def test_mixed_size_batch_is_split_between_the_message_kernels(weights, sampler_weights):
-    """One batch with an 82-, a 127- and a 218-atom system: the tcgen05 kernel (stages <= ~110 atoms), the warp-MMA
-    kernel (<= ~190) and the row-tiled kernel each take the systems they fit -- one oversized system must not push the
-    rest of the batch off the fast path.  Every system's rows are bit-identical to running that system alone (same
-    kernel, same summation order), outputs agree with the fp64 oracle, and the sampler's row-selected tail gives the
-    same positions as the full forward."""
+def test_t5_kernel_takes_a_182_atom_system(weights):
+    """6x6x5 slab (182 atoms): beyond the four-buffer variant of the tcgen05 kernel (<= 114 atoms) but inside the
+    two-buffer one (<= 199, possible since the weights live in tensor memory): one engine, t5, no row mask; graph
+    bit-exact, outputs to 1e-5 of fp64 and of the warp-MMA kernel's (measured 3e-6)."""
     _reset_sticky_pbc()
     m = PaiNN(None, 0, 1, so3_denoising=True).to("cuda:0").eval()
+    m.load_state_dict(weights, strict=True)
+    b = S.collate([S.make_system(17, size=(6, 6, 5)), S.make_system(18, size=(6, 6, 5))])
+    assert int(b.natoms[0]) == 182
+    g = O.generate_graph_values(b.pos.numpy(), b.cell.numpy(), b.natoms)
+    o64 = O.painn_forward(weights, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms, graph=g, dtype=torch.float64)
+    bd = b.clone().to("cuda:0")
+    outs = m(bd)
+    engines = m._message_engines(m._plan_cache)
+    assert [(e[0], e[2]) for e in engines] == [("t5", None)]
+    for got, ref in zip(outs, o64):
+        assert float((got.double().cpu() - ref).abs().max() / ref.abs().max()) < FEATURE_TOL
+    m2 = PaiNN(None, 0, 1, so3_denoising=True).to("cuda:0").eval()
+    m2.msg = "mma"
+    m2.load_state_dict(weights, strict=True)
+    for got, ref in zip(outs, m2(bd)):
+        assert float((got - ref).abs().max() / ref.abs().max()) < FEATURE_TOL
+
+
+@pytest.mark.parametrize("t5_max_atoms", [None, 111])
+def test_mixed_size_batch_is_split_between_the_message_kernels(weights, sampler_weights, t5_max_atoms):
+    """One batch with an 82-, a 127- and a 218-atom system.  The tcgen05 kernel stages a whole system in shared memory
+    (<= 199 atoms; four operand buffers up to 114 atoms, two beyond), the row-tiled kernel takes the rest; with the t5
+    kernel capped at 111 atoms (round 2's limit) the warp-MMA kernel (<= ~190) takes the middle one.  One oversized
+    system must not push the rest of the batch off the fast path.  Every system's rows are bit-identical to running that
+    system alone (same kernel, same summation order), outputs agree with the fp64 oracle, and the sampler's row-selected
+    tail gives the same positions as the full forward."""
+    _reset_sticky_pbc()
+    m = PaiNN(None, 0, 1, so3_denoising=True).to("cuda:0").eval()
+    m.t5_max_atoms = t5_max_atoms
     m.load_state_dict(weights, strict=True)
     parts = [S.make_system(3), S.make_system(41, size=(5, 5, 5)), S.make_system(31, size=(6, 6, 6))]
     b = S.collate(parts)
     nat = [int(v) for v in b.natoms]
-    assert nat[0] <= 111 < nat[1] <= 190 < nat[2]
+    assert nat[0] <= 111 < nat[1] <= 190 < 199 < nat[2]
     f1, f2 = m(b.clone().to("cuda:0"))
     engines = m._message_engines(m._plan_cache)
-    assert [e[0] for e in engines] == ["t5", "mma", "simt"] and all(e[2] is not None for e in engines)
+    expected = ["t5", "mma", "simt"] if t5_max_atoms else ["t5", "simt"]
+    assert [e[0] for e in engines] == expected and all(e[2] is not None for e in engines)
     o64 = O.painn_forward(weights, b.atomic_numbers, b.pos.numpy(), b.cell.numpy(), b.natoms, dtype=torch.float64)
     for got, ref in zip((f1, f2), o64):
         assert float((got.double().cpu() - ref).abs().max() / ref.abs().max()) < FEATURE_TOL
