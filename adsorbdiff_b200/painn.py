@@ -261,9 +261,20 @@ class PaiNN(nn.Module):
                 f"num_rbf={self.num_rbf}, max_neighbors={self.max_neighbors}, cutoff={self.cutoff})")
 
     # ------------------------------------------------------------------ planning
+    def _host_copy(self, name: str, dev_value):
+        """The host copy of `data.<name>` registered by a caller that moved the batch to the device itself
+        (`train.TrainStep.to_device`), if `dev_value` is that very tensor; else None (the plan then reads the device
+        tensor, which waits for the stream)."""
+        hm = getattr(self, "_host_meta", None)
+        if hm and name in hm and hm[name][0] is dev_value and hm[name][1] is not None:
+            return hm[name][1]
+        return None
+
     def _resolve_pbc(self, data):
         pbc_attr = getattr(data, "pbc", None)
         if pbc_attr is not None:
+            host = self._host_copy("pbc", pbc_attr)
+            pbc_attr = host if host is not None else pbc_attr
             p = torch.atleast_2d(torch.as_tensor(pbc_attr)).bool().cpu()
             for i in range(3):
                 if not bool(p[:, i].any()):
@@ -309,7 +320,8 @@ class PaiNN(nn.Module):
         p = _Plan()
         p.natoms_ref, p.cell_ref, p.pbc_ref = natoms, cell, pbc_attr
         p.natoms_ver, p.cell_ver, p.device = natoms._version, cell._version, dev
-        nat = natoms.detach().to("cpu", torch.int64)
+        nat_host = self._host_copy("natoms", natoms)
+        nat = (nat_host if nat_host is not None else natoms).detach().to("cpu", torch.int64)
         p.B = int(nat.numel())
         p.N = int(nat.sum())
         p.n_max = int(nat.max())
@@ -317,10 +329,11 @@ class PaiNN(nn.Module):
             raise _cabi.AdkError(f"system with {p.n_max} atoms exceeds ADK_MAX_ATOMS_PER_SYSTEM")
         off = torch.zeros(p.B + 1, dtype=torch.int32)
         off[1:] = torch.cumsum(nat, 0).to(torch.int32)
-        p.atom_off = off.to(dev)
+        p.atom_off = off.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else off.to(dev)
         p.natoms_cpu = nat
         p.pbc = self._resolve_pbc(data)
-        p.rep = self._cell_repeats(cell.detach().float(), p.pbc)
+        cell_host = self._host_copy("cell", cell)   # (same fp32 torch ops on the host copy: no device round trip)
+        p.rep = self._cell_repeats((cell_host if cell_host is not None else cell).detach().float().reshape(-1, 3, 3), p.pbc)
         p.num_images = (2 * p.rep[0] + 1) * (2 * p.rep[1] + 1) * (2 * p.rep[2] + 1)
         k = self.max_neighbors
         if _cabi.load().adk_neighbors_smem_bytes(p.n_max, p.num_images, k) < 0:
@@ -379,7 +392,10 @@ class PaiNN(nn.Module):
         # the buffer must really be that.)
         lib = _cabi.load()
         off = self.radial_basis.rbf.offset
-        uniform = bool(torch.equal(off.detach().cpu(), torch.linspace(0.0, 1.0, self.num_rbf)))
+        ukey = (off.data_ptr(), off._version)   # (checked once per buffer state: the read waits for the stream)
+        if getattr(self, "_uniform_key", None) != ukey:
+            self._uniform_key, self._uniform = ukey, bool(torch.equal(off.detach().cpu(), torch.linspace(0.0, 1.0, self.num_rbf)))
+        uniform = self._uniform
         t5_ok = self.num_rbf == 128 and F % 64 == 0 and p.B * (F // 64) >= self.t5_min_ctas and uniform
         mma_ok = self.num_rbf % 16 == 0 and 16 <= self.num_rbf <= 128
 

@@ -685,7 +685,9 @@ def run_train(args):
     def one(i):
         # every step's loss is read on the host (the reference logs loss.item() every step) -- one step late, through
         # TrainStep.read_loss, so that the read does not drain the stream the next step is already queued on
-        step(hosts[i % len(hosts)].to(dev, non_blocking=True))
+        # (the HOST batch goes in: TrainStep.to_device copies it to the GPU without touching it -- `SystemBatch.to`
+        # itself moves a batch in place, like PyG's -- and keeps the plan's metadata on the host)
+        step(hosts[i % len(hosts)])
         if step.step_count > 1:
             losses.append(step.read_loss(lag=1))
 

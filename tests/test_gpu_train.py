@@ -217,6 +217,28 @@ def test_train_step_reduces_loss_and_updates_ema(net):
     assert torch.isfinite(out.pos).all() and torch.equal(w_live, net.message_layers[0].rbf_proj.weight)
 
 
+def test_train_step_takes_a_host_batch_without_touching_it(net, weights):
+    """`TrainStep(host_batch)` copies the batch to the GPU itself, keeps the plan's metadata (atoms per system, cell,
+    adsorbate rows) on the host -- no device -> host read in the step -- and leaves the caller's batch alone.  Same
+    generator seed => the same loss, bit for bit, as the step on a batch the caller moved to the device."""
+    tables = T.IGSO3Tables("cuda:0")
+    optim = dict(lr_initial=1e-6, denoising_pos_params=PARAMS, clip_grad_norm=100)
+    host = S.make_batch(5, first_id=20)
+    pos0 = host.pos.clone()
+    losses = []
+    for from_host in (True, False):
+        net.load_state_dict(weights, strict=True)
+        step = T.TrainStep(net, optim, tables, generator=torch.Generator(device="cuda").manual_seed(3))
+        b = host if from_host else host.clone().to("cuda:0")
+        losses.append(float(step(b)))
+        if from_host:
+            assert host.pos.device.type == "cpu" and torch.equal(host.pos, pos0)
+            p = net._train_plan
+            assert net._host_meta["natoms"][0] is p.natoms_ref and net._host_meta["natoms"][1] is host.natoms
+            assert p.natoms_cpu.tolist() == host.natoms.tolist()
+    assert losses[0] == losses[1], losses
+
+
 def test_train_step_on_one_system_and_on_a_large_one(net):
     """Degenerate batch shapes of the step: a single system (one row chunk per few rows, GEMMs on the narrow tiles) and a
     218-atom slab (more rows than any sampler test, row degree up to 100)."""
