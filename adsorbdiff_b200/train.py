@@ -38,6 +38,19 @@ INV_SQRT_2 = 1.0 / math.sqrt(2.0)
 # --------------------------------------------------------------------------------------------------------------
 # message op under autograd
 # --------------------------------------------------------------------------------------------------------------
+def rbf_weight_scale(net, w: torch.Tensor, refresh: bool = False) -> float:
+    """Power-of-two prescale of an `rbf_proj` weight for its fp16x2 planes: s * max|w| in [1024, 2048], 32x below the
+    fp16 limit.  Measured on the host the first time a weight is seen (one device read) and again whenever `TrainStep`
+    reads the status word (`status_every` steps): an optimiser step moves a weight by at most lr, so the headroom
+    cannot be used up in between; should it ever be, the split sets the overflow bit and `check_gemm_status` raises."""
+    tab = net.__dict__.setdefault("_train_rbf_scale", {})
+    key = w.data_ptr()
+    if refresh or key not in tab:
+        amax = float(w.detach().abs().max())
+        tab[key] = 2.0 ** math.floor(math.log2(SPLIT_TARGET / amax)) if amax > 0 and math.isfinite(amax) else 1.0
+    return tab[key]
+
+
 class MessageFn(torch.autograd.Function):
     """(x, vec, xh, W_rbf, b_rbf) -> ((x + dx) / sqrt(2), vec + dvec); PaiNNMessage + residual
     (painn_denoising.py:443-445, 534-567).  `vec` may be None (first layer)."""
@@ -49,9 +62,21 @@ class MessageFn(torch.autograd.Function):
         vec_in = vec.detach().contiguous() if vec is not None else None
         vec_out = torch.empty(N, 3, F_, dtype=torch.float32, device=x.device)
         xh_c, w_c, b_c = xh.detach().contiguous(), w.detach().contiguous(), b.detach().contiguous()
-        call("adk_message", p.device, None, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(xh_c),
-             ptr(vec_in), ptr(w_c), ptr(b_c), ptr(net.radial_basis.rbf.offset), N, F_, R, float(net.cutoff),
-             net.radial_basis.exponent, ptr(x_out), ptr(vec_out))
+        if getattr(net, "train_msg", "t5") == "t5" and getattr(p, "t5_fits", False):
+            # the sampler's tcgen05 kernel (csrc/message_t5.cu): fp16x2 planes of the weight at a power-of-two scale
+            # measured on the weight itself (`rbf_weight_scale`), overflow reported through the training status word
+            scale = rbf_weight_scale(net, w_c)
+            planes = torch.empty(2 * w_c.numel(), dtype=torch.float16, device=x.device)
+            status = _TcWorkspace.get(x.device).status
+            call("adk_split_f16", p.device, ptr(w_c), R, 3 * F_, R, scale, ptr(planes), 3 * F_, ptr(status))
+            call("adk_message_t5", p.device, ptr(p.atom_off), p.B, p.n_max, None, ptr(p.row_start), ptr(p.row_deg),
+                 ptr(p.e_src), ptr(p.e_geo), ptr(xh_c), ptr(vec_in), ptr(planes), scale, ptr(b_c),
+                 ptr(net.radial_basis.rbf.offset), F_, R, float(net.cutoff), net.radial_basis.exponent,
+                 float(net.msg_t5_comp), ptr(x_out), ptr(vec_out), None, 0, 1.0, ptr(status))
+        else:   # exact-fp32 row-tiled kernel (any system size, any num_rbf)
+            call("adk_message", p.device, None, ptr(p.row_start), ptr(p.row_deg), ptr(p.e_src), ptr(p.e_geo), ptr(xh_c),
+                 ptr(vec_in), ptr(w_c), ptr(b_c), ptr(net.radial_basis.rbf.offset), N, F_, R, float(net.cutoff),
+                 net.radial_basis.exponent, ptr(x_out), ptr(vec_out))
         ctx.net, ctx.p, ctx.has_vec = net, p, vec is not None
         ctx.save_for_backward(xh_c, vec_in if vec_in is not None else xh_c.new_empty(0), w_c, b_c)
         return x_out, vec_out
@@ -715,6 +740,8 @@ class TrainStep:
         left by an operand that already holds inf / nan; the status word says so (read every `status_every` steps)."""
         ws = _TcWorkspace.get(self.params[0].device)
         st = int(ws.status.item())
+        for m in self.net.message_layers:   # (the stream is drained anyway: re-measure the message weights' prescales)
+            rbf_weight_scale(self.net, m.rbf_proj.weight, refresh=True)
         if st:
             ws.status.zero_()
             raise _cabi.AdkOverflow("a GEMM operand of the training step was not finite (fp16x2 split overflow bit set): "

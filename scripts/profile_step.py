@@ -3,7 +3,10 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from adsorbdiff_b200 import PaiNN, _cabi, synthetic as S
+from adsorbdiff_b200 import _cabi
+if os.environ.get("ADK_LIB"):
+    _cabi._LIB_PATH = os.environ["ADK_LIB"]
+from adsorbdiff_b200 import PaiNN, synthetic as S
 from adsorbdiff_b200.denoiser import schedule_table
 
 systems = int(sys.argv[1]) if len(sys.argv) > 1 else 256

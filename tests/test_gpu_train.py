@@ -36,11 +36,13 @@ def _oracle_grads(weights, b, G1, G2, dtype=torch.float64):
     return P, o1.detach(), o2.detach()
 
 
-@pytest.mark.parametrize("name,gemm", [("tiny", "tc"), ("tiny", "torch"), ("jit2", "tc"), ("jit2", "torch"), ("mixed", "tc")])
-def test_backward_matches_oracle(name, gemm, net, weights):
+@pytest.mark.parametrize("name,gemm,msg", [("tiny", "tc", "t5"), ("tiny", "torch", "simt"), ("jit2", "tc", "t5"), ("jit2", "tc", "simt"),
+                                           ("jit2", "torch", "t5"), ("mixed", "tc", "t5")])
+def test_backward_matches_oracle(name, gemm, msg, net, weights):
     """`gemm`: the nn.Linear layers' three GEMMs on the tcgen05 kernel with device-side prescales ("tc", the default)
-    or on cuBLAS fp32 through torch ("torch")."""
-    net.train_gemm = gemm
+    or on cuBLAS fp32 through torch ("torch").  `msg`: the message forward on the sampler's tcgen05 kernel ("t5", the
+    default wherever every system fits it) or on the exact-fp32 row-tiled kernel ("simt")."""
+    net.train_gemm, net.train_msg = gemm, msg
     b = CASES[name][0]()
     g = torch.Generator().manual_seed(1)
     G1, G2 = torch.randn(b.pos.shape[0], 3, generator=g), torch.randn(b.pos.shape[0], 3, generator=g)
@@ -69,7 +71,7 @@ def test_backward_matches_oracle(name, gemm, net, weights):
         if err32 > worst32[1]:
             worst32 = (k, err32)
         checked += 1
-    print(f"{name}/{gemm}: {checked} gradients; cuda-vs-fp64 worst {worst[0]} {worst[1]:.2e}; "
+    print(f"{name}/{gemm}/{msg}: {checked} gradients; cuda-vs-fp64 worst {worst[0]} {worst[1]:.2e}; "
           f"fp32 torch autograd (CPU oracle)-vs-fp64 worst {worst32[0]} {worst32[1]:.2e}")
     assert checked >= 60 and worst[1] <= GRAD_TOL and worst[1] <= 2 * max(worst32[1], 5e-6), (worst, worst32)
 
