@@ -759,6 +759,10 @@ def main():
     ap.add_argument("--train-batch", type=int, default=TRAIN_BATCH, help="systems per GPU for --train")
     ap.add_argument("--train-ref-batch", type=int, default=TRAIN_BATCH, help="batch of the reference_gpu leg of --train")
     args = ap.parse_args()
+    if os.environ.get("BENCH_WATCHDOG"):
+        # debugging aid: dump every thread's Python stack and exit if the run is still going after that many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
     if args.train:
         run_train(args)
     elif args.impl == "reference":
