@@ -13,7 +13,8 @@
 // system, read as 32 consecutive words per warp, i.e. conflict free -- and keeps the segmented sums of the
 // target rows in registers.  No atomics, no shuffles, deterministic; per-edge tensors never exist in HBM.
 //
-// Two phases per CTA, so that weights (64 KB) + sources + operand tiles fit the 227 KB of shared memory:
+// Two phases per CTA (one weight tile -- the MMA's A operand, resident in tensor memory -- and one set of sources in
+// shared memory at a time):
 //   A: W rows = [m1 slice | m3 slice]   lanes 0-63 accumulate dx, lanes 64-127 the m3 * r_hat part of dvec
 //   B: W rows = [m2 slice | m2 slice]   lanes 0-63 take row slots 0-3 of a tile, lanes 64-127 slots 4-7; the
 //                                       source is p2 = xh2 * vec (3 components), formed while staging
@@ -21,9 +22,11 @@
 // of each, the t-th chunk of 16 edges in distance order.  Edges of equal rank have similar distances, so the
 // Gaussian windows (16 centres each) of a tile overlap and only the 16..64 centres of their union enter the
 // MMA (K = 128 dense otherwise); a tile whose union exceeds 64 centres is issued as two k-halves into the same
-// accumulator.  Warp roles: warp 0 = TMA (weights) + MMA issue + TMEM owner; warps 4-7 = generators (one
-// column each: CSR record -> basis values -> fp16x2 -> UMMA 128-byte-swizzled operand row, plus the per-column
-// metadata); four epilogue warpgroups, each taking two of a tile's eight rows and keeping their sums in registers.
+// accumulator.  Warp roles: warp 0 = MMA issue + TMEM owner; two generator warpgroups on alternate tiles (one
+// column per thread: CSR record -> basis values -> fp16x2 -> UMMA 128-byte-swizzled operand row, plus the per-column
+// metadata); four epilogue warpgroups in two teams on alternate tiles, each warpgroup taking half of a tile's eight
+// rows and keeping their sums in registers; the epilogue warpgroups also write the weight rows to TMEM at the start
+// of a phase (tcgen05.st, thread = lane = weight row).
 #include <cuda.h>
 #include <cuda_fp16.h>
 

@@ -237,7 +237,7 @@ class PaiNN(nn.Module):
         # "tc": tcgen05 fp16x2-split GEMMs (fp32 parity, see csrc/linear_tc.cu); "fp32": exact-fp32 SIMT GEMMs
         self.gemm = "tc"
         # message kernel: "t5" = tcgen05 / TMEM / TMA kernel with the system's sources staged in shared memory
-        # (csrc/message_t5.cu; needs num_rbf == 128, hidden % 64 == 0 and systems of <= ~110 atoms -- anything else
+        # (csrc/message_t5.cu; needs num_rbf == 128, hidden % 64 == 0 and systems of <= 199 atoms -- anything else
         # falls through to "mma", then "simt"); "mma" = per-system staged, rbf_proj as
         # warp-level mma.sync micro-GEMMs (csrc/message_mma.cu); "simt" = 16-tap FFMA2 kernel (csrc/message.cu)
         self.msg = "t5"
@@ -385,8 +385,8 @@ class PaiNN(nn.Module):
         p.tab_xh = torch.empty(ne, 3 * F, **f32)
         p.tab_spx = torch.zeros(2 * p.tab_rows * F, **f16)
         p.tab_sph = torch.zeros(2 * p.tab_rows * F, **f16)
-        # Message kernels by system size: the tcgen05 kernel stages a whole system's sources in shared memory (up to ~110
-        # atoms), the warp-MMA kernel up to ~190, the row-tiled SIMT kernel anything.  A batch is split between them
+        # Message kernels by system size: the tcgen05 kernel stages a whole system's sources in shared memory (up to 199
+        # atoms), the warp-MMA kernel up to ~190 (other num_rbf / hidden sizes), the row-tiled SIMT kernel anything.  A batch is split between them
         # system by system (`p.engines`: [(name, n_cap, per-atom 0/1 mask or None)]); one oversized system does not take
         # the rest of the batch off the fast path.  (t5 evaluates the Gaussian centres arithmetically as k / (R - 1):
         # the buffer must really be that.)

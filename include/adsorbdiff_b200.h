@@ -237,10 +237,12 @@ int adk_message_mma(const int32_t* atom_off, int B, int n_max,
 
 /*
  * tcgen05 variant of adk_message_mma, the default for full batches (csrc/message_t5.cu): one CTA per (system,
- * 64-feature slice); D[feature][edge] = W . rbf^T by tcgen05.mma into TMEM (fp16x2 split, banded K), weights by
- * TMA, sources of the whole system staged in shared memory, epilogue threads own one feature (= TMEM lane) and
- * reduce the CSR rows in registers.  Same arithmetic contract as adk_message; requires R == 128, F % 64 == 0 and a
- * system that fits (adk_message_t5_smem_bytes > 0), else the caller uses adk_message_mma / adk_message.
+ * 64-feature slice); D[feature][edge] = W . rbf^T by tcgen05.mma into TMEM (fp16x2 split, banded K), the weight
+ * tile as the TMEM-resident A operand (tcgen05.st once per phase), sources of the whole system staged in shared
+ * memory, epilogue threads own one feature (= TMEM lane) and reduce the CSR rows in registers.  Same arithmetic
+ * contract as adk_message; requires R == 128, F % 64 == 0 and a system that fits (adk_message_t5_smem_bytes > 0:
+ * up to 199 atoms at F = 512; four operand buffers up to 114 atoms, two beyond), else the caller uses
+ * adk_message_mma / adk_message.
  *   w_rbf_split = fp16 [2][3F][R] planes of w_rbf scaled by w_scale (adk_split_f16_multi)
  */
 int64_t adk_message_t5_smem_bytes(int R, int n_max);
