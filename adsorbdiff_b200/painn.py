@@ -233,7 +233,9 @@ class PaiNN(nn.Module):
         self._scales: Optional[dict] = None   # calibrated fp16x2 prescales (see `calibrate`); None = class defaults
         self._calib: Optional[dict] = None    # while calibrating: id(linear) -> max |input|
         self.auto_calibrate = True
-        self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, "_scales", None))
+        # loaded weights invalidate every measured prescale (the sampler's and the training step's message weights')
+        self.register_load_state_dict_post_hook(
+            lambda module, incompatible: (setattr(module, "_scales", None), module.__dict__.pop("_train_rbf_scale", None)))
         # "tc": tcgen05 fp16x2-split GEMMs (fp32 parity, see csrc/linear_tc.cu); "fp32": exact-fp32 SIMT GEMMs
         self.gemm = "tc"
         # message kernel: "t5" = tcgen05 / TMEM / TMA kernel with the system's sources staged in shared memory

@@ -44,7 +44,7 @@ def rbf_weight_scale(net, w: torch.Tensor, refresh: bool = False) -> float:
     reads the status word (`status_every` steps): an optimiser step moves a weight by at most lr, so the headroom
     cannot be used up in between; should it ever be, the split sets the overflow bit and `check_gemm_status` raises."""
     tab = net.__dict__.setdefault("_train_rbf_scale", {})
-    key = w.data_ptr()
+    key = (w.data_ptr(), tuple(w.shape))   # (the table is dropped by `load_state_dict` and rebuilt by `TrainStep.__init__`)
     if refresh or key not in tab:
         amax = float(w.detach().abs().max())
         tab[key] = 2.0 ** math.floor(math.log2(SPLIT_TARGET / amax)) if amax > 0 and math.isfinite(amax) else 1.0
@@ -662,6 +662,7 @@ class TrainStep:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.step_count = 0
         self.status_every = int(optim.get("status_every", 50))   # host read of the GEMMs' overflow word (one sync)
+        net.__dict__.pop("_train_rbf_scale", None)                # message-weight prescales: measured again on first use
         # loss read-out without draining the stream: each step copies its loss to a pinned ring slot right after the
         # forward and records an event; `read_loss(lag)` waits for that event only
         self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == "cuda" else None
@@ -745,7 +746,9 @@ class TrainStep:
         if st:
             ws.status.zero_()
             raise _cabi.AdkOverflow("a GEMM operand of the training step was not finite (fp16x2 split overflow bit set): "
-                                    "loss or gradients have diverged")
+                                    "loss or gradients have diverged -- or an rbf_proj weight grew 32x within "
+                                    f"{self.status_every} steps and left the prescale of the message forward "
+                                    "(train.rbf_weight_scale; re-measured just now)")
 
     def params_in_sync(self) -> bool:
         """Data parallel sanity: every rank holds bit-identical parameters (they start equal and see the same averaged

@@ -2,6 +2,7 @@
 (oracle/gen_golden.py::training_goldens: rot_utils._expansion/_score/sample/score_vec/score_norm,
 sde_denoising_trainer.tr_so3_schedule/_compute_loss executed from the reference tree) and against the oracle
 restatement.  Everything here is torch on the CPU: the kernels are not involved."""
+import math
 import os
 
 import numpy as np
@@ -137,6 +138,45 @@ def test_com_only_noising_matches_reference(case):
     np.testing.assert_allclose(nb.ads_center_noise_vec.numpy(), ref["ads_center_noise_vec"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(nb.tr_score.numpy(), ref["tr_score"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(nb.pos.numpy(), ref["pos"], atol=2e-5)
+
+
+def test_host_found_adsorbate_rows_give_the_same_noising_and_loss(tables):
+    """`TrainStep.to_device` finds the adsorbate rows on the host copy and hands them over as index tensors
+    (`_ads_idx`, `_ads_seg`), so that noising and loss index with them instead of a boolean mask (whose size the host
+    would have to wait for).  Same draws => the same noised batch and the same loss, bit for bit."""
+    outs = []
+    for with_rows in (False, True):
+        b = CASES["mixed"][0]()
+        if with_rows:
+            b._ads_idx = torch.nonzero(b.tags == 2).flatten()
+            b._ads_seg = b.batch.index_select(0, b._ads_idx)
+        idx, seg = T._adsorbate_rows(b)
+        assert torch.equal(idx, torch.nonzero(b.tags == 2).flatten()) and torch.equal(seg, b.batch[b.tags == 2])
+        nb = T.tr_so3_schedule(b, PARAMS, tables, generator=torch.Generator().manual_seed(11))
+        g = torch.Generator().manual_seed(12)
+        out = (torch.randn(nb.pos.shape[0], 3, generator=g), torch.randn(nb.pos.shape[0], 3, generator=g))
+        outs.append((nb.pos.clone(), nb.tr_score.clone(), nb.rot_score.clone(), T.denoising_loss(out, nb, tables)))
+    for a, c in zip(*outs):
+        assert torch.equal(a, c)
+
+
+def test_rbf_weight_scale_is_a_power_of_two_with_headroom():
+    """Prescale of the message weights for the tcgen05 forward of the training step: s * max|w| in (1024, 2048]."""
+    class Net:
+        pass
+    net = Net()
+    keep = []   # (the table is keyed on the weight's storage: keep the tensors alive, as parameters are)
+    for k, mag in enumerate((3e-4, 0.07, 1.0, 55.0)):
+        w = torch.randn(1536, 128, generator=torch.Generator().manual_seed(k)) * mag
+        keep.append(w)
+        s = T.rbf_weight_scale(net, w)
+        assert math.log2(s) == round(math.log2(s)) and 1024 < s * float(w.abs().max()) <= 2048
+        assert T.rbf_weight_scale(net, w) == s
+    w = torch.full((4, 4), 0.01)
+    s0 = T.rbf_weight_scale(net, w)
+    w.mul_(64)                                   # the weight grew: the cached scale stays until a refresh
+    assert T.rbf_weight_scale(net, w) == s0 and T.rbf_weight_scale(net, w, refresh=True) == s0 / 64
+    assert T.rbf_weight_scale(net, torch.zeros(3, 3)) == 1.0
 
 
 def test_schedule_statistics(tables):
