@@ -156,6 +156,12 @@ def _first_systems(data, k: int):
     return sub
 
 
+def _drop_measured_scales(module, incompatible_keys) -> None:
+    """load_state_dict post-hook (must return None)"""
+    module._scales = None
+    module.__dict__.pop("_train_rbf_scale", None)
+
+
 class PaiNN(nn.Module):
     def __init__(
         self,
@@ -234,8 +240,7 @@ class PaiNN(nn.Module):
         self._calib: Optional[dict] = None    # while calibrating: id(linear) -> max |input|
         self.auto_calibrate = True
         # loaded weights invalidate every measured prescale (the sampler's and the training step's message weights')
-        self.register_load_state_dict_post_hook(
-            lambda module, incompatible: (setattr(module, "_scales", None), module.__dict__.pop("_train_rbf_scale", None)))
+        self.register_load_state_dict_post_hook(_drop_measured_scales)
         # "tc": tcgen05 fp16x2-split GEMMs (fp32 parity, see csrc/linear_tc.cu); "fp32": exact-fp32 SIMT GEMMs
         self.gemm = "tc"
         # message kernel: "t5" = tcgen05 / TMEM / TMA kernel with the system's sources staged in shared memory
